@@ -1,0 +1,182 @@
+"""Deterministic synthetic hashgraph traces.
+
+A trace is the *global* view of a gossip run in index space: event ``i`` has a
+self-parent ``p0[i]``, an other-parent ``p1[i]`` (both ``-1`` for a member's
+root event), a creator ``creator[i]`` (member id ``0..M-1``), a float64
+timestamp ``t[i]`` and a 64-byte signature ``sig[i]``.  Events are listed in a
+topological (arrival) order, so ``p0[i] < i`` and ``p1[i] < i``.
+
+The generators reproduce the shape of what the reference simulation produces
+(``/root/reference/swirld.py:315-345``: a random member syncs with a random
+*other* member and creates one event whose parents are the two heads), without
+crypto:
+
+* G1 ``gossip``       -- the reference sim's process (swirld.py:323, 341-344).
+* G2 ``adversarial``  -- G1 restricted to two cliques with a small cross-clique
+  probability (delayed fame, coin rounds) plus stale other-parents ("near
+  forks": an other-parent that is 1..7 events behind the peer's head; still a
+  valid event per swirld.py:103-108, never a true fork).
+* G3 ``tick``         -- tick-synchronous: every tick each member creates one
+  event on a random peer's previous-tick head (frontier width == M).
+
+Everything is pure ``random.Random(seed)`` + ``hashlib.blake2b`` so that the
+same trace is rebuilt bit-for-bit here, in the golden-fixture script and on the
+GPU box.
+"""
+from __future__ import annotations
+
+import hashlib
+import random
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class Trace:
+    """SoA view of a hashgraph; the layout the engine keeps in HBM."""
+    M: int
+    p0: np.ndarray        # int32[N]  self-parent index, -1 for roots
+    p1: np.ndarray        # int32[N]  other-parent index, -1 for roots
+    creator: np.ndarray   # int32[N]  member id
+    t: np.ndarray         # float64[N] creation time (swirld.py:91)
+    sig: np.ndarray       # uint8[N,64] signature bytes (swirld.py:92)
+    name: str = ""
+
+    @property
+    def N(self) -> int:
+        return int(self.p0.shape[0])
+
+    def slice(self, a: int, b: int) -> "Trace":
+        return Trace(self.M, self.p0[a:b], self.p1[a:b], self.creator[a:b],
+                     self.t[a:b], self.sig[a:b], self.name)
+
+
+def make_sigs(seed: int, n: int) -> np.ndarray:
+    """sig[i] = blake2b(b'sig<seed>:<i>', 64 bytes) -- stands in for the
+    Ed25519 signature whose bytes the hot path consumes (swirld.py:272, 281)."""
+    out = np.empty((n, 64), dtype=np.uint8)
+    for i in range(n):
+        out[i] = np.frombuffer(
+            hashlib.blake2b(b"sig%d:%d" % (seed, i), digest_size=64).digest(),
+            dtype=np.uint8)
+    return out
+
+
+def _finish(M, p0, p1, cr, seed, name, tied=0) -> Trace:
+    n = len(p0)
+    if tied:
+        t = (np.arange(n, dtype=np.int64) // tied).astype(np.float64)
+    else:
+        t = np.arange(n, dtype=np.float64)
+    return Trace(M, np.asarray(p0, dtype=np.int32), np.asarray(p1, dtype=np.int32),
+                 np.asarray(cr, dtype=np.int32), t, make_sigs(seed, n), name)
+
+
+def gossip(M: int, N: int, seed: int = 1, tied: int = 0) -> Trace:
+    """G1: events 0..M-1 are the roots (creator == index); afterwards a random
+    member ``a`` syncs with a random other member ``b`` and creates an event
+    with parents (head[a], head[b])."""
+    assert M >= 2 and N >= M
+    rng = random.Random(seed)
+    p0 = [-1] * M
+    p1 = [-1] * M
+    cr = list(range(M))
+    head = list(range(M))
+    for i in range(M, N):
+        a = rng.randrange(M)
+        b = rng.randrange(M - 1)
+        b += (b >= a)
+        p0.append(head[a])
+        p1.append(head[b])
+        cr.append(a)
+        head[a] = i
+    return _finish(M, p0, p1, cr, seed, "G1(M=%d,N=%d,seed=%d)" % (M, N, seed), tied)
+
+
+def adversarial(M: int, N: int, seed: int = 1, p_cross: float = 0.02,
+                p_stale: float = 0.3, tied: int = 0) -> Trace:
+    """G2: two cliques (members < M/2 and >= M/2).  The peer is drawn from the
+    creator's own clique unless a ``p_cross`` coin says otherwise; with
+    probability ``p_stale`` the other-parent is not the peer's head but an
+    event 1..7 steps back on the peer's self-parent chain (clamped at the
+    peer's root)."""
+    assert M >= 4 and N >= M
+    rng = random.Random(seed)
+    half = M // 2
+    p0 = [-1] * M
+    p1 = [-1] * M
+    cr = list(range(M))
+    head = list(range(M))
+    for i in range(M, N):
+        a = rng.randrange(M)
+        lo, hi = (0, half) if a < half else (half, M)
+        if rng.random() < p_cross:
+            lo, hi = (half, M) if a < half else (0, half)
+            b = lo + rng.randrange(hi - lo)
+        else:
+            b = lo + rng.randrange(hi - lo - 1)
+            b += (b >= a)
+        other = head[b]
+        if rng.random() < p_stale:
+            back = 1 + rng.randrange(7)
+            while back > 0 and p0[other] >= 0:
+                other = p0[other]
+                back -= 1
+        p0.append(head[a])
+        p1.append(other)
+        cr.append(a)
+        head[a] = i
+    return _finish(M, p0, p1, cr, seed,
+                   "G2(M=%d,N=%d,seed=%d,pc=%g,ps=%g)" % (M, N, seed, p_cross, p_stale), tied)
+
+
+def tick(M: int, N: int, seed: int = 1) -> Trace:
+    """G3: tick-synchronous gossip; in tick k every member (in a random order)
+    creates one event whose other-parent is a random peer's tick k-1 event."""
+    assert M >= 2 and N >= M
+    rng = random.Random(seed)
+    p0 = [-1] * M
+    p1 = [-1] * M
+    cr = list(range(M))
+    prev = list(range(M))
+    i = M
+    while i < N:
+        cur = list(prev)
+        order = list(range(M))
+        rng.shuffle(order)
+        for a in order:
+            if i >= N:
+                break
+            b = rng.randrange(M - 1)
+            b += (b >= a)
+            p0.append(prev[a])
+            p1.append(prev[b])
+            cr.append(a)
+            cur[a] = i
+            i += 1
+        prev = cur
+    return _finish(M, p0, p1, cr, seed, "G3(M=%d,N=%d,seed=%d)" % (M, N, seed))
+
+
+def chunks(n: int, k: int):
+    """The call schedule: consecutive [first, first+count) slices of K events,
+    one (divide_rounds, decide_fame, find_order) triple per slice
+    (swirld.py:324-328).  The final order depends on it."""
+    first = 0
+    while first < n:
+        cnt = min(k, n - first)
+        yield first, cnt
+        first += cnt
+
+
+def heights(tr: Trace) -> np.ndarray:
+    """Topological level of each event (swirld.py:114-120)."""
+    h = np.zeros(tr.N, dtype=np.int32)
+    p0, p1 = tr.p0.tolist(), tr.p1.tolist()
+    hl = [0] * tr.N
+    for i in range(tr.N):
+        if p0[i] >= 0:
+            hl[i] = max(hl[p0[i]], hl[p1[i]]) + 1
+    h[:] = hl
+    return h
