@@ -1,0 +1,495 @@
+// swirld_b200.cu -- host side of libswirld_b200.so: the C ABI of include/swirld_b200.h
+// over the kernels in swirld_kernels.cuh.  No torch, no CPU compute path: every
+// consensus result is produced by a kernel; the host only validates the graph shape
+// on append (what Node.is_valid_event checks, swirld.py:104-108), keeps the
+// creator/height/chain-position mirrors it needs for that, and moves bytes.
+#include "swirld_kernels.cuh"
+#include "../../include/swirld_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string g_create_error;
+
+struct TimedSpan { cudaEvent_t a, b; int cat; };
+
+}  // namespace
+
+struct sw_engine {
+    int M = 0, NC = 1, cap = 0, C = 6, device = 0, Rcap = 0;
+    bool unit = true;
+    i64 tot = 0;
+    std::vector<i64> h_stake;
+    // host mirrors for validation / views
+    std::vector<int32_t> h_creator, h_height, h_head, h_count, h_seq_stage;
+    int n_events = 0, n_divided = 0, n_tx = 0;
+    // device columns
+    int32_t *d_p0 = nullptr, *d_p1 = nullptr, *d_creator = nullptr, *d_seq = nullptr;
+    double *d_t = nullptr;
+    uint8_t *d_sig = nullptr;
+    int32_t *d_row = nullptr, *d_round = nullptr;
+    u64 *d_T = nullptr, *d_SM = nullptr;
+    uint8_t *d_wit = nullptr;
+    int8_t *d_famous_ev = nullptr;
+    // per round
+    int32_t *d_W = nullptr, *d_rem = nullptr, *d_newc = nullptr;
+    u64 *d_S = nullptr, *d_V = nullptr;
+    int8_t *d_famous = nullptr;
+    uint8_t *d_consensus = nullptr, *d_done = nullptr;
+    i64 *d_stake = nullptr;
+    int32_t *d_scal = nullptr;
+    // find_order
+    int32_t *d_lastord = nullptr, *d_tx = nullptr, *d_idx = nullptr, *d_batch_ev = nullptr,
+            *d_batch_seg = nullptr, *d_seg_start = nullptr, *d_seg_fw = nullptr, *d_seg_nf = nullptr,
+            *d_perm = nullptr, *d_rounds_in = nullptr;
+    uint8_t *d_seg_white = nullptr;
+    double *d_ts = nullptr;
+    u64 *d_key = nullptr;
+    int seg_cap = 0;
+    void *d_flush = nullptr;
+    size_t flush_bytes = 0;
+    int32_t *h_scal = nullptr;    // pinned
+    int32_t *h_newc = nullptr;    // pinned, Rcap
+    cudaStream_t stream = nullptr;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> pool;
+    sw_stats_t stats{};
+    std::string err;
+};
+
+namespace {
+
+int fail(sw_engine *e, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t _s = (call);                                                         \
+        if (_s != cudaSuccess)                                                           \
+            return fail(e, SW_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_s),   \
+                        __FILE__, __LINE__);                                             \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+cudaEvent_t get_event(sw_engine *e) {
+    if (!e->pool.empty()) { cudaEvent_t ev = e->pool.back(); e->pool.pop_back(); return ev; }
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    return ev;
+}
+
+struct Span {
+    sw_engine *e; TimedSpan s;
+    Span(sw_engine *e_, int cat) : e(e_) { s.a = get_event(e); s.b = get_event(e); s.cat = cat; cudaEventRecord(s.a, e->stream); }
+    ~Span() { cudaEventRecord(s.b, e->stream); e->spans.push_back(s); }
+};
+
+void fold_spans(sw_engine *e) {
+    for (auto &s : e->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            if (s.cat == 0) e->stats.ms_divide_rounds += ms;
+            else if (s.cat == 1) e->stats.ms_decide_fame += ms;
+            else if (s.cat == 2) e->stats.ms_find_order += ms;
+        }
+        e->pool.push_back(s.a); e->pool.push_back(s.b);
+    }
+    e->spans.clear();
+}
+
+int device_error(sw_engine *e) {     // after a sync: did a kernel flag an error?
+    int code = e->h_scal[SC_ERR];
+    if (code < 0) {
+        const char *what = code == SW_E_CAPACITY ? "round table exhausted"
+                         : code == SW_E_INDEX ? "list index out of range (swirld.py:305: a single seer)"
+                         : code == SW_E_KEY ? "KeyError (undecided witness in a consensus round)" : "device error";
+        return fail(e, code, "%s", what);
+    }
+    return 0;
+}
+
+int reset_state(sw_engine *e) {
+    const size_t RM = (size_t)e->Rcap * e->M;
+    k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_W, -1, RM);
+    CK(cudaMemsetAsync(e->d_famous, 0xff, RM, e->stream));
+    CK(cudaMemsetAsync(e->d_S, 0, RM * sizeof(u64), e->stream));
+    CK(cudaMemsetAsync(e->d_consensus, 0, e->Rcap, e->stream));
+    CK(cudaMemsetAsync(e->d_famous_ev, 0xff, e->cap, e->stream));
+    k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_idx, -1, (size_t)e->cap);
+    k_fill_i32<<<1, 64, 0, e->stream>>>(e->d_lastord, -1, (size_t)e->M);
+    int32_t sc[SC_COUNT] = {0};
+    sc[SC_MAX_ROUND] = -1;
+    CK(cudaMemcpyAsync(e->d_scal, sc, sizeof sc, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->stats.kernel_launches += 3;
+    e->n_events = e->n_divided = e->n_tx = 0;
+    std::fill(e->h_head.begin(), e->h_head.end(), -1);
+    std::fill(e->h_count.begin(), e->h_count.end(), 0);
+    memset(e->h_scal, 0, sizeof(int32_t) * SC_COUNT);
+    return 0;
+}
+
+template <int NC>
+int launch_divide(sw_engine *e, const DivParams &P) {
+    static bool attr_set[2] = {false, false};
+    const size_t smem = sizeof(DivSmem<NC>);
+    if (!attr_set[NC - 1]) {
+        CK(cudaFuncSetAttribute(k_divide<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[NC - 1] = true;
+    }
+    k_divide<NC><<<1, 1024, smem, e->stream>>>(P);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sw_version(void) { return 100; }
+
+const char *sw_last_error(const sw_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period, int device,
+              sw_engine **out) {
+    sw_engine *e = nullptr;
+    if (!out) return fail(e, SW_E_ARG, "out is NULL");
+    *out = nullptr;
+    if (M < 1 || capacity_events < 1 || coin_period < 1) return fail(e, SW_E_ARG, "bad M / capacity / coin period");
+    if (M > SW_MAX_MEMBERS) return fail(e, SW_E_UNSUPPORTED, "M=%d > %d members not supported by this build", M, SW_MAX_MEMBERS);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(e, SW_E_CUDA, "no CUDA device (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(e, SW_E_ARG, "device %d out of range (%d devices)", device, ndev);
+    e = new sw_engine();
+    e->M = M; e->NC = (M + 31) / 32; e->cap = capacity_events; e->C = coin_period; e->device = device;
+    e->h_stake.resize(M);
+    for (int c = 0; c < M; c++) {
+        e->h_stake[c] = stake ? stake[c] : 1;
+        if (e->h_stake[c] < 0) { delete e; return fail(nullptr, SW_E_ARG, "negative stake"); }
+        if (e->h_stake[c] != 1) e->unit = false;
+        e->tot += e->h_stake[c];
+    }
+    // a round other than the last needs more than 2*tot/3 members with a witness (quirk Q3)
+    i64 per = std::min<i64>(M, (2 * e->tot) / 3 + 1);
+    if (per < 1) per = 1;
+    e->Rcap = (int)std::min<i64>((i64)e->cap + 2, (i64)e->cap / per + 16);
+    e->h_head.assign(M, -1);
+    e->h_count.assign(M, 0);
+    e->h_creator.reserve(e->cap);
+    e->h_height.reserve(e->cap);
+    int rc = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        const size_t cap = e->cap, RM = (size_t)e->Rcap * M;
+        CK(dalloc(&e->d_p0, cap)); CK(dalloc(&e->d_p1, cap)); CK(dalloc(&e->d_creator, cap)); CK(dalloc(&e->d_seq, cap));
+        CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64));
+        CK(dalloc(&e->d_row, cap * M)); CK(dalloc(&e->d_T, cap * M)); CK(dalloc(&e->d_SM, cap));
+        CK(dalloc(&e->d_round, cap)); CK(dalloc(&e->d_wit, cap)); CK(dalloc(&e->d_famous_ev, cap));
+        CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_S, RM)); CK(dalloc(&e->d_V, RM)); CK(dalloc(&e->d_famous, RM));
+        CK(dalloc(&e->d_consensus, (size_t)e->Rcap)); CK(dalloc(&e->d_done, (size_t)e->Rcap));
+        CK(dalloc(&e->d_rem, (size_t)e->Rcap)); CK(dalloc(&e->d_newc, (size_t)e->Rcap));
+        CK(dalloc(&e->d_stake, (size_t)M)); CK(dalloc(&e->d_scal, (size_t)SC_COUNT));
+        CK(dalloc(&e->d_lastord, (size_t)64)); CK(dalloc(&e->d_tx, cap)); CK(dalloc(&e->d_idx, cap));
+        CK(dalloc(&e->d_batch_ev, cap)); CK(dalloc(&e->d_batch_seg, cap)); CK(dalloc(&e->d_perm, 2 * cap));
+        CK(dalloc(&e->d_ts, cap)); CK(dalloc(&e->d_key, cap * 8));
+        CK(cudaMallocHost((void **)&e->h_scal, sizeof(int32_t) * SC_COUNT));
+        CK(cudaMallocHost((void **)&e->h_newc, sizeof(int32_t) * e->Rcap));
+        CK(cudaMemcpyAsync(e->d_stake, e->h_stake.data(), sizeof(i64) * M, cudaMemcpyHostToDevice, e->stream));
+        return reset_state(e);
+    }();
+    if (rc < 0) { g_create_error = e->err; sw_destroy(e); return rc; }
+    memset(&e->stats, 0, sizeof e->stats);
+    *out = e;
+    return SW_OK;
+}
+
+void sw_destroy(sw_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    fold_spans(e);
+    for (auto ev : e->pool) cudaEventDestroy(ev);
+    void *ptrs[] = {e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
+                    e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_V, e->d_famous, e->d_consensus,
+                    e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
+                    e->d_batch_ev, e->d_batch_seg, e->d_perm, e->d_ts, e->d_key, e->d_seg_start, e->d_seg_fw,
+                    e->d_seg_nf, e->d_seg_white, e->d_rounds_in, e->d_flush};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (e->h_scal) cudaFreeHost(e->h_scal);
+    if (e->h_newc) cudaFreeHost(e->h_newc);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int sw_reset(sw_engine *e) {
+    if (!e) return SW_E_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    fold_spans(e);
+    e->h_creator.clear(); e->h_height.clear();
+    int rc = reset_state(e);
+    memset(&e->stats, 0, sizeof e->stats);
+    return rc;
+}
+
+int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const int32_t *creator,
+              const double *t, const uint8_t *sig) {
+    if (!e || n < 0 || (n > 0 && (!p0 || !p1 || !creator || !t || !sig))) return fail(e, SW_E_ARG, "bad argument");
+    if (n == 0) return SW_OK;
+    if ((i64)e->n_events + n > e->cap) return fail(e, SW_E_CAPACITY, "capacity_events=%d exceeded", e->cap);
+    CK(cudaSetDevice(e->device));
+    const int base = e->n_events;
+    // graph-shape checks of is_valid_event (swirld.py:104-108) + the fork-free contract
+    std::vector<int32_t> head_save(e->h_head), count_save(e->h_count);
+    e->h_seq_stage.resize(n);
+    e->h_creator.resize((size_t)base + n);
+    e->h_height.resize((size_t)base + n);
+    int rc = SW_OK;
+    for (int j = 0; j < n && rc == SW_OK; j++) {
+        const int i = base + j, c = creator[j], a = p0[j], b = p1[j];
+        if (c < 0 || c >= e->M) { rc = fail(e, SW_E_ARG, "event %d: creator %d out of range", i, c); break; }
+        if (a < 0 && b < 0) {
+            if (e->h_head[c] >= 0) { rc = fail(e, SW_E_FORK, "event %d: second root of member %d", i, c); break; }
+            e->h_height[i] = 0;                                          // swirld.py:117-118
+        } else {
+            if (a < 0 || b < 0 || a >= i || b >= i) { rc = fail(e, SW_E_PARENT, "event %d: parents (%d,%d) unknown", i, a, b); break; }
+            if (e->h_creator[a] != c) { rc = fail(e, SW_E_PARENT, "event %d: self-parent %d has another creator", i, a); break; }
+            if (e->h_creator[b] == c) { rc = fail(e, SW_E_PARENT, "event %d: other-parent %d has the same creator", i, b); break; }
+            if (e->h_head[c] != a) { rc = fail(e, SW_E_FORK, "event %d: self-parent %d is not member %d's latest event (fork)", i, a, c); break; }
+            e->h_height[i] = std::max(e->h_height[a], e->h_height[b]) + 1;   // swirld.py:120
+        }
+        e->h_creator[i] = c;
+        e->h_head[c] = i;
+        e->h_seq_stage[j] = e->h_count[c]++;
+    }
+    if (rc != SW_OK) {
+        e->h_head = head_save; e->h_count = count_save;
+        e->h_creator.resize(base); e->h_height.resize(base);
+        return rc;
+    }
+    CK(cudaMemcpyAsync(e->d_p0 + base, p0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_p1 + base, p1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_creator + base, creator, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_t + base, t, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_sig + (size_t)base * 64, sig, (size_t)64 * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_seq + base, e->h_seq_stage.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    // h_seq_stage is reused by the next append: the copy above must have left the host buffer
+    CK(cudaStreamSynchronize(e->stream));
+    e->stats.h2d_bytes += (i64)n * (4 * 4 + 8 + 64);
+    e->stats.events += n;
+    e->n_events += n;
+    return SW_OK;
+}
+
+int sw_divide_rounds(sw_engine *e, int first, int n) {
+    if (!e || n < 0) return fail(e, SW_E_ARG, "bad argument");
+    if (n == 0) return SW_OK;
+    if (first != e->n_divided) return fail(e, SW_E_ARG, "divide_rounds: first=%d but %d events are divided (events must arrive in order)", first, e->n_divided);
+    if (first + n > e->n_events) return fail(e, SW_E_KEY, "divide_rounds: events [%d,%d) not appended", first, first + n);
+    CK(cudaSetDevice(e->device));
+    DivParams P{};
+    P.M = e->M; P.first = first; P.n = n; P.Rcap = e->Rcap;
+    P.p0 = e->d_p0; P.p1 = e->d_p1; P.creator = e->d_creator;
+    P.row = e->d_row; P.T = e->d_T; P.SM = e->d_SM; P.round = e->d_round; P.wit = e->d_wit; P.W = e->d_W;
+    P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.scal = e->d_scal;
+    StrongParams Q{};
+    Q.M = e->M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
+    Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
+    {
+        Span sp(e, 0);
+        int rc = e->NC == 1 ? launch_divide<1>(e, P) : launch_divide<2>(e, P);
+        if (rc < 0) return rc;
+        const int wpb = 8, blocks = (n + wpb - 1) / wpb;
+        if (e->NC == 1) k_strong<1><<<blocks, wpb * 32, 0, e->stream>>>(Q);
+        else k_strong<2><<<blocks, wpb * 32, 0, e->stream>>>(Q);
+        CK(cudaGetLastError());
+    }
+    e->stats.kernel_launches += 2;
+    e->stats.events_divided += n;
+    e->n_divided += n;
+    return SW_OK;
+}
+
+int sw_decide_fame(sw_engine *e, int32_t *new_c_out, int cap) {
+    if (!e || cap < 0 || (cap > 0 && !new_c_out)) return fail(e, SW_E_ARG, "bad argument");
+    CK(cudaSetDevice(e->device));
+    if (e->n_divided == 0) return fail(e, SW_E_ARG, "decide_fame: no witnesses yet (max() of an empty dict, swirld.py:225)");
+    FameParams P{};
+    P.M = e->M; P.Rcap = e->Rcap; P.C = e->C; P.W = e->d_W; P.S = e->d_S; P.famous = e->d_famous;
+    P.famous_ev = e->d_famous_ev; P.consensus = e->d_consensus; P.done = e->d_done; P.rem = e->d_rem; P.V = e->d_V;
+    P.sig = e->d_sig; P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.newc = e->d_newc; P.scal = e->d_scal;
+    {
+        Span sp(e, 1);
+        k_fame<<<1, 1024, 0, e->stream>>>(P);
+        CK(cudaGetLastError());
+    }
+    e->stats.kernel_launches += 1;
+    CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    fold_spans(e);
+    e->stats.d2h_bytes += sizeof(int32_t) * SC_COUNT;
+    int rc = device_error(e);
+    if (rc < 0) return rc;
+    const int cnt = e->h_scal[SC_NEWC];
+    if (cnt > cap) return fail(e, SW_E_ARG, "decide_fame: %d new consensus rounds do not fit cap=%d", cnt, cap);
+    if (cnt > 0) {
+        CK(cudaMemcpyAsync(e->h_newc, e->d_newc, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        memcpy(new_c_out, e->h_newc, sizeof(int32_t) * cnt);
+        e->stats.d2h_bytes += sizeof(int32_t) * cnt;
+    }
+    return cnt;
+}
+
+int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
+    if (!e || n < 0 || (n > 0 && !new_c)) return fail(e, SW_E_ARG, "bad argument");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    std::vector<int32_t> rs(new_c, new_c + n);
+    std::sort(rs.begin(), rs.end());                                  // sorted(new_c), swirld.py:283
+    for (int r : rs) if (r < 0 || r >= e->Rcap) return fail(e, SW_E_KEY, "find_order: unknown round %d", r);
+    if (n > e->seg_cap) {
+        int nc = std::max(n, std::max(64, 2 * e->seg_cap));
+        for (void *p : {(void *)e->d_seg_start, (void *)e->d_seg_fw, (void *)e->d_seg_nf, (void *)e->d_seg_white, (void *)e->d_rounds_in})
+            if (p) cudaFree(p);
+        CK(dalloc(&e->d_seg_start, (size_t)nc + 1)); CK(dalloc(&e->d_seg_fw, (size_t)nc * 64));
+        CK(dalloc(&e->d_seg_nf, (size_t)nc)); CK(dalloc(&e->d_seg_white, (size_t)nc * 64));
+        CK(dalloc(&e->d_rounds_in, (size_t)nc));
+        e->seg_cap = nc;
+    }
+    CK(cudaMemcpyAsync(e->d_rounds_in, rs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    OrderParams P{};
+    P.M = e->M; P.Rcap = e->Rcap; P.nrounds = n; P.rounds = e->d_rounds_in; P.W = e->d_W; P.famous = e->d_famous;
+    P.row = e->d_row; P.p0 = e->d_p0; P.creator = e->d_creator; P.seq = e->d_seq; P.t = e->d_t; P.sig = e->d_sig;
+    P.stake = e->d_stake; P.tot = e->tot; P.lastord = e->d_lastord; P.batch_ev = e->d_batch_ev; P.batch_seg = e->d_batch_seg;
+    P.seg_start = e->d_seg_start; P.seg_fw = e->d_seg_fw; P.seg_nf = e->d_seg_nf; P.seg_white = e->d_seg_white;
+    P.ts = e->d_ts; P.key = e->d_key; P.perm = e->d_perm; P.tx = e->d_tx; P.idx = e->d_idx; P.tx_base = e->n_tx; P.scal = e->d_scal;
+    cudaEvent_t a = get_event(e), b = get_event(e);
+    cudaEventRecord(a, e->stream);
+    k_order_plan<<<1, 64, 0, e->stream>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));      // rs (host vector) was consumed by the copy above
+    e->stats.kernel_launches += 1;
+    e->stats.h2d_bytes += sizeof(int32_t) * n;
+    e->stats.d2h_bytes += sizeof(int32_t) * SC_COUNT;
+    int rc = device_error(e);
+    const int nbatch = e->h_scal[SC_BATCH];
+    if (rc == 0 && nbatch > 0) {
+        const int wpb = 8;
+        k_order_times<<<(nbatch + wpb - 1) / wpb, wpb * 32, 0, e->stream>>>(P, nbatch);
+        k_order_sort<<<n, 1024, 0, e->stream>>>(P);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
+        e->stats.kernel_launches += 2;
+    }
+    cudaEventRecord(b, e->stream);
+    e->spans.push_back(TimedSpan{a, b, 2});
+    CK(cudaStreamSynchronize(e->stream));
+    fold_spans(e);
+    if (rc == 0) rc = device_error(e);
+    if (rc < 0) return rc;
+    e->n_tx += nbatch;
+    return nbatch;
+}
+
+int sw_n_events(const sw_engine *e) { return e ? e->n_events : SW_E_ARG; }
+int sw_n_divided(const sw_engine *e) { return e ? e->n_divided : SW_E_ARG; }
+int sw_n_transactions(const sw_engine *e) { return e ? e->n_tx : SW_E_ARG; }
+
+int sw_sync(sw_engine *e) {
+    if (!e) return SW_E_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    fold_spans(e);
+    return device_error(e);
+}
+
+int sw_max_round(sw_engine *e) {
+    int rc = sw_sync(e);
+    if (rc < 0) return rc;
+    return e->h_scal[SC_MAX_ROUND];
+}
+
+int sw_stats(sw_engine *e, sw_stats_t *out) {
+    if (!e || !out) return SW_E_ARG;
+    int rc = sw_sync(e);
+    *out = e->stats;
+    return rc;
+}
+
+#define GETTER(NAME, TYPE, SRC, LIMIT, WIDTH)                                                        \
+    int NAME(sw_engine *e, int first, int n, TYPE *out) {                                            \
+        if (!e || first < 0 || n < 0 || (n > 0 && !out)) return fail(e, SW_E_ARG, "bad argument");  \
+        if (first + n > (LIMIT)) return fail(e, SW_E_KEY, #NAME ": [%d,%d) out of range", first, first + n); \
+        if (n == 0) return SW_OK;                                                                    \
+        CK(cudaSetDevice(e->device));                                                                \
+        CK(cudaMemcpyAsync(out, (SRC) + (size_t)first * (WIDTH), sizeof(TYPE) * (size_t)n * (WIDTH), \
+                           cudaMemcpyDeviceToHost, e->stream));                                     \
+        CK(cudaStreamSynchronize(e->stream));                                                        \
+        e->stats.d2h_bytes += sizeof(TYPE) * (size_t)n * (WIDTH);                                    \
+        return SW_OK;                                                                                \
+    }
+
+GETTER(sw_get_round, int32_t, e->d_round, e->n_divided, 1)
+GETTER(sw_get_witness_flags, uint8_t, e->d_wit, e->n_divided, 1)
+GETTER(sw_get_famous, int8_t, e->d_famous_ev, e->n_events, 1)
+GETTER(sw_get_can_see, int32_t, e->d_row, e->n_divided, e->M)
+GETTER(sw_get_witness_table, int32_t, e->d_W, e->Rcap, e->M)
+GETTER(sw_get_transactions, int32_t, e->d_tx, e->n_tx, 1)
+GETTER(sw_get_idx, int32_t, e->d_idx, e->n_events, 1)
+
+int sw_get_height(sw_engine *e, int first, int n, int32_t *out) {
+    if (!e || first < 0 || n < 0 || (n > 0 && !out)) return fail(e, SW_E_ARG, "bad argument");
+    if (first + n > e->n_events) return fail(e, SW_E_KEY, "sw_get_height: out of range");
+    memcpy(out, e->h_height.data() + first, sizeof(int32_t) * n);
+    return SW_OK;
+}
+
+int sw_get_consensus(sw_engine *e, int32_t *out, int cap) {
+    if (!e || cap < 0) return fail(e, SW_E_ARG, "bad argument");
+    int mr = sw_max_round(e);
+    if (mr < -1) return mr;
+    std::vector<uint8_t> flags((size_t)mr + 2);
+    if (mr >= 0) {
+        CK(cudaMemcpyAsync(flags.data(), e->d_consensus, (size_t)mr + 1, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->stats.d2h_bytes += mr + 1;
+    }
+    int cnt = 0;
+    for (int r = 0; r <= mr; r++)
+        if (flags[r]) { if (cnt < cap) out[cnt] = r; cnt++; }
+    return cnt;
+}
+
+int sw_flush_l2(sw_engine *e, int64_t bytes) {
+    if (!e || bytes <= 0) return SW_E_ARG;
+    CK(cudaSetDevice(e->device));
+    if ((size_t)bytes > e->flush_bytes) {
+        if (e->d_flush) cudaFree(e->d_flush);
+        e->d_flush = nullptr;
+        CK(cudaMalloc(&e->d_flush, (size_t)bytes));
+        e->flush_bytes = (size_t)bytes;
+    }
+    CK(cudaMemsetAsync(e->d_flush, 0x5a, (size_t)bytes, e->stream));
+    return SW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,595 @@
+// swirld_kernels.cuh -- hand-written sm_100a kernels of the virtual-voting engine.
+//
+// Kernel math (fork-free graphs, event id == arrival index, proven against the
+// literal oracle by tests/engine_model.py before being written here):
+//
+//   row(h)[c]  = can_see[h][c]  (swirld.py:72, 203-205, 220)  = max(row(p0)[c], row(p1)[c]),
+//                own column := h.  -1 = absent.
+//   W[r][c]    = witnesses[r][c] (swirld.py:61, 197, 222), -1 = absent.
+//   SM(h)      = { c_ : W[round h][c_] >= 0  and  row(h)[c_] >= W[round h][c_] }   (M-bit mask)
+//   T(h)[c_]   = { c  : h sees a round-(round h) event k of member c, and k sees W[round h][c_] }
+//              -- the transposed "strongly sees" matrix of swirld.py:207-214.  Inside one
+//              round it obeys  T(h) = T(p0) | T(p1) | (SM(h) bit c_) << creator(h), parents of a
+//              lower round contribute 0, and a promoted event restarts from its own term.
+//   hits[c_]   = stake-weight of (T(p0)[c_] | T(p1)[c_])           (swirld.py:209-214)
+//   promoted   = 3 * #{c_ : 3*hits[c_] > 2*tot} > 2*tot            (swirld.py:216, quirk Q3)
+//
+// All of it is integer / bit work; there is no GEMM here and no tensor-core use.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+#define SW_RING 256          // events whose row/T/round stay in shared memory
+#define SW_RING_WINS (SW_RING / 32)
+#define SW_WC 16             // rounds of the witness table cached in shared memory
+
+enum { SC_MAX_ROUND = 0, SC_ERR = 1, SC_NEWC = 2, SC_BATCH = 3, SC_NSEG = 4, SC_COUNT = 8 };
+
+struct DivParams {
+    int M, first, n, Rcap;
+    const int32_t *p0, *p1, *creator;
+    int32_t *row;        // [cap][M]
+    u64 *T;              // [cap][M]
+    u64 *SM;             // [cap]
+    int32_t *round;      // [cap]
+    uint8_t *wit;        // [cap]
+    int32_t *W;          // [Rcap][M]
+    const i64 *stake;    // [M]
+    i64 tot2;            // 2 * total stake
+    int unit;            // all stakes == 1
+    int32_t *scal;       // SC_*
+};
+
+// ---------------------------------------------------------------- small helpers
+__device__ __forceinline__ unsigned ld_acquire_shared(const unsigned *p) {
+    unsigned v;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared(unsigned *p, unsigned v) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ i64 wsum(u64 m, int unit, const i64 *stake_s) {
+    if (unit) return (i64)__popcll(m);
+    i64 s = 0;
+    while (m) {
+        int b = __ffsll((long long)m) - 1;
+        s += stake_s[b];
+        m &= m - 1;
+    }
+    return s;
+}
+
+template <int NC>
+struct DivSmem {
+    int32_t row[SW_RING][NC * 32];
+    u64 T[SW_RING][NC * 32];
+    int32_t round[SW_RING];
+    unsigned done[SW_RING];
+    int32_t Wc[SW_WC][NC * 32];
+    i64 stake[NC * 32];
+    int rmaxp[2];
+};
+
+// ---------------------------------------------------------------- K1+K2: divide_rounds
+// One CTA of 32 warps walks the events [first, first+n) in windows of 32 consecutive
+// indices, one warp per event, lane = member column (NC columns per lane).  Inside a
+// window a warp spins on its parents' per-event "done" flags in shared memory (acquire /
+// release at CTA scope); dependencies always point to lower indices, so the window always
+// drains.  The last SW_RING events' rows, T matrices and rounds live in a shared-memory
+// ring (parents are almost always recent heads); older parents come from L2/HBM.
+template <int NC>
+__global__ void __launch_bounds__(1024, 1) k_divide(DivParams P) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    DivSmem<NC> &S = *reinterpret_cast<DivSmem<NC> *>(smraw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = P.M;
+    constexpr int MS = NC * 32;
+
+    for (int i = tid; i < SW_RING; i += 1024) S.done[i] = 0;
+    if (tid < MS) S.stake[tid] = tid < M ? P.stake[tid] : 0;
+    int rmax = P.scal[SC_MAX_ROUND];
+    int wbase = max(0, rmax - (SW_WC / 2 - 1));
+    if (tid < 2) S.rmaxp[tid] = rmax;
+    for (int i = tid; i < SW_WC * MS; i += 1024) {
+        int slot = i / MS, c = i % MS;
+        int r = wbase + ((slot - (wbase % SW_WC) + SW_WC) % SW_WC);
+        S.Wc[slot][c] = (c < M && r < P.Rcap) ? P.W[(size_t)r * M + c] : -1;
+    }
+    __syncthreads();
+
+    const int w_first = P.first >> 5, w_last = (P.first + P.n - 1) >> 5;
+    for (int win = w_first; win <= w_last; ++win) {
+        const int h = win * 32 + warp;
+        if (h >= P.first && h < P.first + P.n) {
+            const int pa = __ldg(P.p0 + h), pb = __ldg(P.p1 + h), cr = __ldg(P.creator + h);
+            int rowh[NC];
+            u64 t[NC];
+            int r, ra = -1;
+            bool promoted;
+            if (pa < 0) {                       // root (swirld.py:195-198)
+#pragma unroll
+                for (int j = 0; j < NC; j++) { rowh[j] = -1; t[j] = 0; }
+                r = -1; promoted = true;        // round 0, own term only
+            } else {
+                const bool a_sm = pa >= P.first && (win - (pa >> 5)) < SW_RING_WINS;
+                const bool b_sm = pb >= P.first && (win - (pb >> 5)) < SW_RING_WINS;
+                const int sa = pa & (SW_RING - 1), sb = pb & (SW_RING - 1);
+                if (a_sm && (pa >> 5) == win)
+                    while (ld_acquire_shared(&S.done[sa]) != (unsigned)(pa + 1)) { }
+                if (b_sm && (pb >> 5) == win)
+                    while (ld_acquire_shared(&S.done[sb]) != (unsigned)(pb + 1)) { }
+                ra = a_sm ? S.round[sa] : __ldcg(P.round + pa);
+                const int rb = b_sm ? S.round[sb] : __ldcg(P.round + pb);
+                r = max(ra, rb);                                        // swirld.py:200
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const int c = lane + 32 * j;
+                    int va = -1, vb = -1;
+                    u64 ta = 0, tb = 0;
+                    if (c < M) {
+                        va = a_sm ? S.row[sa][c] : __ldcg(P.row + (size_t)pa * M + c);
+                        vb = b_sm ? S.row[sb][c] : __ldcg(P.row + (size_t)pb * M + c);
+                        if (ra == r) ta = a_sm ? S.T[sa][c] : __ldcg(P.T + (size_t)pa * M + c);
+                        if (rb == r) tb = b_sm ? S.T[sb][c] : __ldcg(P.T + (size_t)pb * M + c);
+                    }
+                    rowh[j] = max(va, vb);                              // swirld.py:203-205
+                    t[j] = ta | tb;
+                }
+                int cnt = 0;
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const i64 hits = wsum(t[j], P.unit, S.stake);       // swirld.py:209-214
+                    cnt += __popc(__ballot_sync(0xffffffffu, 3 * hits > P.tot2));
+                }
+                promoted = 3 * (i64)cnt > P.tot2;                       // swirld.py:216
+            }
+            int rh = r + (promoted ? 1 : 0);                            // swirld.py:217-219
+            const bool wit = (pa < 0) || rh > ra;                       // swirld.py:221 / 196-197
+            if (rh >= P.Rcap) { if (lane == 0) atomicMin(&P.scal[SC_ERR], -5); rh = P.Rcap - 1; }
+            const bool w_sm = rh >= wbase && rh < wbase + SW_WC;
+            if (wit && lane == 0) {                                      // swirld.py:222
+                P.W[(size_t)rh * M + cr] = h;
+                if (w_sm) S.Wc[rh % SW_WC][cr] = h;
+                atomicMax(&S.rmaxp[win & 1], rh);
+            }
+            __syncwarp();
+            u64 smask = 0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const int c = lane + 32 * j;
+                if (c == cr) rowh[j] = h;                                // swirld.py:220
+                int w = -1;
+                if (c < M) w = w_sm ? S.Wc[rh % SW_WC][c] : __ldcg(P.W + (size_t)rh * M + c);
+                const bool sm = (c < M) && w >= 0 && rowh[j] >= w;
+                smask |= (u64)__ballot_sync(0xffffffffu, sm) << (32 * j);
+                const u64 th = (promoted ? 0ull : t[j]) | (sm ? (1ull << cr) : 0ull);
+                if (c < M) {
+                    const int sh = h & (SW_RING - 1);
+                    S.row[sh][c] = rowh[j];
+                    S.T[sh][c] = th;
+                    P.row[(size_t)h * M + c] = rowh[j];
+                    P.T[(size_t)h * M + c] = th;
+                }
+            }
+            if (lane == 0) {
+                S.round[h & (SW_RING - 1)] = rh;
+                P.round[h] = rh;
+                P.wit[h] = wit ? 1 : 0;
+                P.SM[h] = smask;
+            }
+            __syncwarp();
+            if (lane == 0) st_release_shared(&S.done[h & (SW_RING - 1)], (unsigned)(h + 1));
+        }
+        __syncthreads();
+        rmax = max(rmax, S.rmaxp[win & 1]);
+        const int nb = max(wbase, rmax - (SW_WC / 2 - 1));
+        if (nb != wbase) {                      // uniform: every thread sees the same rmax
+            for (int i = tid; i < SW_WC * MS; i += 1024) {
+                int slot = i / MS, c = i % MS;
+                int ro = wbase + ((slot - (wbase % SW_WC) + SW_WC) % SW_WC);
+                int rn = nb + ((slot - (nb % SW_WC) + SW_WC) % SW_WC);
+                if (rn != ro)
+                    S.Wc[slot][c] = (c < M && rn < P.Rcap) ? __ldcg(P.W + (size_t)rn * M + c) : -1;
+            }
+            wbase = nb;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) P.scal[SC_MAX_ROUND] = rmax;
+}
+
+// ---------------------------------------------------------------- K3-prep: strongly-seen sets
+// decide_fame's s(y) (swirld.py:245-254) for every witness y among [first, first+n):
+// hits[c_] = sum over members c whose latest seen event k = row(y)[c] has round EXACTLY
+// round(y)-1 (quirk Q15) of stake[c] * [c_ in SM(k)];  S[round y][creator y] = {c_ : 3 hits > 2 tot}.
+struct StrongParams {
+    int M, first, n, Rcap;
+    const int32_t *creator, *row, *round;
+    const uint8_t *wit;
+    const u64 *SM;
+    u64 *S;              // [Rcap][M]
+    const i64 *stake;
+    i64 tot2;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256) k_strong(StrongParams P) {
+    const int lane = threadIdx.x & 31;
+    const int h = P.first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    if (h >= P.first + P.n) return;
+    if (!P.wit[h]) return;
+    const int rh = P.round[h];
+    if (rh < 1 || rh >= P.Rcap) return;
+    const int M = P.M, r = rh - 1;
+    u64 mk[NC];
+    i64 st[NC], hits[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const int c = lane + 32 * j;
+        mk[j] = 0; st[j] = 0; hits[j] = 0;
+        if (c < M) {
+            const int k = P.row[(size_t)h * M + c];
+            if (k >= 0 && P.round[k] == r) mk[j] = P.SM[k];
+            st[j] = P.stake[c];
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < NC; jj++) {
+        for (int l = 0; l < 32; l++) {
+            if (jj * 32 + l >= M) break;
+            const u64 m = __shfl_sync(0xffffffffu, mk[jj], l);
+            if (m == 0) continue;
+            const i64 s = __shfl_sync(0xffffffffu, st[jj], l);
+#pragma unroll
+            for (int j = 0; j < NC; j++)
+                if ((m >> (lane + 32 * j)) & 1) hits[j] += s;
+        }
+    }
+    u64 smask = 0;
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+        smask |= (u64)__ballot_sync(0xffffffffu, 3 * hits[j] > P.tot2) << (32 * j);
+    if (lane == 0) P.S[(size_t)rh * M + P.creator[h]] = smask;
+}
+
+// ---------------------------------------------------------------- K3: decide_fame
+// One CTA; voter rounds are a true sequential dependency (votes of round r_ read the
+// votes of round r_-1), candidates are independent: one thread per undecided witness
+// slot (r, member), looping over the <= M voters of the round held in shared memory.
+// V[r][mx] = mask over voter members "voted True on witness (r,mx)" in the previous
+// voter round (the only part of swirld.py:59 `votes` that is ever read again).
+struct FameParams {
+    int M, Rcap, C;
+    const int32_t *W;        // [Rcap][M]
+    const u64 *S;            // [Rcap][M]
+    int8_t *famous;          // [Rcap][M]  -1 undecided
+    int8_t *famous_ev;       // [cap]
+    uint8_t *consensus;      // [Rcap]
+    uint8_t *done;           // [Rcap] scratch
+    int32_t *rem;            // [Rcap] scratch: undecided witnesses of the round
+    u64 *V;                  // [Rcap][M] scratch
+    const uint8_t *sig;      // [cap][64]
+    const i64 *stake;
+    i64 tot2;
+    int unit;
+    int32_t *newc;           // [Rcap] out
+    int32_t *scal;
+};
+
+__global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
+    __shared__ u64 sv[64];
+    __shared__ i64 vsum[64];
+    __shared__ i64 stake_s[64];
+    __shared__ int vw[64];
+    __shared__ int vcoin[64];
+    __shared__ int s_maxc, s_lo;
+    const int tid = threadIdx.x, M = P.M;
+    const int max_r = P.scal[SC_MAX_ROUND];                     // swirld.py:225
+    if (tid < 64) stake_s[tid] = tid < M ? P.stake[tid] : 0;
+    if (tid == 0) {
+        int mc = 0;
+        while (mc < P.Rcap && P.consensus[mc]) mc++;            // swirld.py:226-228
+        s_maxc = mc;
+        P.scal[SC_NEWC] = 0;
+    }
+    __syncthreads();
+    const int max_c = s_maxc;
+    if (max_r < 0) return;
+    for (int r = max_c + tid; r <= max_r; r += 1024) {
+        P.done[r] = 0;
+        int cnt = 0;
+        if (!P.consensus[r])
+            for (int m = 0; m < M; m++)
+                if (P.W[(size_t)r * M + m] >= 0 && P.famous[(size_t)r * M + m] < 0) cnt++;
+        P.rem[r] = cnt;
+    }
+    if (tid == 0) s_lo = max_c;
+    __syncthreads();
+    for (int r_ = max_c + 1; r_ <= max_r; ++r_) {               // iter_voters, swirld.py:238-241
+        if (tid < 64) {
+            int w = tid < M ? P.W[(size_t)r_ * M + tid] : -1;
+            vw[tid] = w;
+            u64 s = w >= 0 ? P.S[(size_t)r_ * M + tid] : 0ull;
+            sv[tid] = s;
+            vcoin[tid] = w >= 0 ? (P.sig[(size_t)w * 64] >> 7) : 0;  // swirld.py:272
+            vsum[tid] = wsum(s, P.unit, stake_s);
+        }
+        if (tid == 0) {
+            int lo = s_lo;
+            while (lo < r_ && P.rem[lo] == 0) lo++;
+            s_lo = lo;
+        }
+        __syncthreads();
+        const int lo = s_lo;
+        const int nslots = (r_ - lo) * M;
+        for (int i = tid; i < nslots; i += 1024) {              // iter_undetermined, :231-236
+            const int r = lo + i / M, mx = i % M;
+            if (P.consensus[r]) continue;
+            const size_t slot = (size_t)r * M + mx;
+            const int x = P.W[slot];
+            if (x < 0 || P.famous[slot] >= 0) continue;
+            const int d = r_ - r;
+            const u64 prev = d > 1 ? P.V[slot] : 0ull;
+            const bool coin_round = (d % P.C) == 0;
+            u64 mask = 0;
+            int decided = -1;
+            for (int m = 0; m < M; m++) {
+                if (vw[m] < 0) continue;
+                const u64 s = sv[m];
+                int vote;
+                if (d == 1) vote = (int)((s >> mx) & 1);         // swirld.py:256-257
+                else {
+                    const i64 yes = wsum(s & prev, P.unit, stake_s);   // majority, :20-27
+                    const i64 no = vsum[m] - yes;
+                    const int v = no > yes ? 0 : 1;
+                    const i64 tt = no > yes ? no : yes;
+                    if (!coin_round) {
+                        if (3 * tt > P.tot2) { if (decided < 0) decided = v; continue; }  // :261-263
+                        vote = v;                                 // :265
+                    } else vote = (3 * tt > P.tot2) ? v : vcoin[m];   // :267-272
+                }
+                mask |= (u64)vote << m;
+            }
+            if (decided >= 0) {
+                P.famous[slot] = (int8_t)decided;
+                P.famous_ev[x] = (int8_t)decided;
+                P.done[r] = 1;
+                atomicSub(&P.rem[r], 1);
+            } else P.V[slot] = mask;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {                                              // swirld.py:274-276
+        int cnt = 0;
+        for (int r = max_c; r <= max_r; r++)
+            if (P.done[r] && P.rem[r] == 0) { P.newc[cnt++] = r; P.consensus[r] = 1; }
+        P.scal[SC_NEWC] = cnt;
+    }
+}
+
+// ---------------------------------------------------------------- K4: find_order
+struct OrderParams {
+    int M, Rcap, nrounds;
+    const int32_t *rounds;       // [nrounds] sorted(new_c)
+    const int32_t *W;
+    const int8_t *famous;
+    const int32_t *row, *p0, *creator, *seq;
+    const double *t;
+    const uint8_t *sig;
+    const i64 *stake;
+    i64 tot;
+    int32_t *lastord;            // [M] latest ordered event per member chain, -1 none
+    // per-call outputs
+    int32_t *batch_ev;           // [cap] events ordered by this call, grouped by segment
+    int32_t *batch_seg;          // [cap] segment of each
+    int32_t *seg_start;          // [nrounds+1]
+    int32_t *seg_fw;             // [nrounds][64] famous witnesses
+    int32_t *seg_nf;             // [nrounds]
+    uint8_t *seg_white;          // [nrounds][64]
+    double *ts;                  // [cap] per batch slot
+    u64 *key;                    // [cap][8] big-endian words of white ^ sig
+    int32_t *perm;               // [cap] scratch
+    int32_t *tx;                 // [cap] transactions
+    int32_t *idx;                // [cap]
+    int tx_base;
+    int32_t *scal;
+};
+
+// Plan: for each new consensus round (ascending, sequential because the "not yet
+// ordered" frontier lastord[] carries over), the famous witnesses f_w, the whitening
+// XOR (swirld.py:284-285) and, per member chain c, the range of events this round
+// orders.  On a fork-free graph the reference's BFS over tbd (swirld.py:288-289) reaches
+// exactly the not-yet-ordered events x with x <= max_{w in f_w & tbd} row(w)[c], and
+// "received" (swirld.py:291-293) is monotone along the chain, so the newly ordered
+// events of chain c are (lastord[c], min(reach, received-threshold)].
+__global__ void __launch_bounds__(64, 1) k_order_plan(OrderParams P) {
+    __shared__ int fw[64];
+    __shared__ int cnts[64];
+    __shared__ int nf_s;
+    const int tid = threadIdx.x, M = P.M;
+    int total = 0;
+    for (int si = 0; si < P.nrounds; ++si) {
+        const int r = P.rounds[si];
+        int w = -1, fam = -1;
+        if (tid < M && r >= 0 && r < P.Rcap) { w = P.W[(size_t)r * M + tid]; fam = P.famous[(size_t)r * M + tid]; }
+        if (w >= 0 && fam < 0) atomicMin(&P.scal[SC_ERR], -3);   // self.famous[w] KeyError, :284
+        const bool isf = w >= 0 && fam == 1;
+        const unsigned b0 = __ballot_sync(0xffffffffu, isf);
+        __shared__ unsigned ball[2];
+        if ((tid & 31) == 0) ball[tid >> 5] = b0;
+        __syncthreads();
+        const int pos = (tid >= 32 ? __popc(ball[0]) : 0) + __popc(b0 & ((1u << (tid & 31)) - 1));
+        if (isf) fw[pos] = w;
+        if (tid == 0) nf_s = __popc(ball[0]) + __popc(ball[1]);
+        __syncthreads();
+        const int nf = nf_s;
+        {   // white = XOR of the famous witnesses' signatures, byte tid
+            uint8_t x = 0;
+            for (int i = 0; i < nf; i++) x ^= P.sig[(size_t)fw[i] * 64 + tid];
+            P.seg_white[(size_t)si * 64 + tid] = x;
+            P.seg_fw[(size_t)si * 64 + tid] = tid < nf ? fw[tid] : -1;
+            if (tid == 0) { P.seg_nf[si] = nf; P.seg_start[si] = total; }
+        }
+        int cnt = 0, cut = -1;
+        if (tid < M) {
+            const int c = tid;
+            int U = -1, thr = -1;
+            for (int i = 0; i < nf; i++) {
+                const int wi = fw[i];
+                const int v = P.row[(size_t)wi * M + c];
+                if (wi > P.lastord[P.creator[wi]]) U = max(U, v);        // w in tbd
+                if (v > thr) {       // is v seen by more than half the stake?  (:291-293)
+                    i64 acc = 0;
+                    for (int k = 0; k < nf; k++)
+                        if (P.row[(size_t)fw[k] * M + c] >= v) acc += P.stake[P.creator[fw[k]]];
+                    if (2 * acc > P.tot) thr = v;
+                }
+            }
+            cut = min(U, thr);
+            const int lo = P.lastord[c];
+            if (cut > lo) cnt = P.seq[cut] - (lo >= 0 ? P.seq[lo] : -1);
+        }
+        cnts[tid] = cnt;
+        __syncthreads();
+        int off = total;
+        for (int i = 0; i < tid; i++) off += cnts[i];
+        int tot_here = 0;
+        for (int i = 0; i < 64; i++) tot_here += cnts[i];
+        if (cnt > 0) {
+            int x = cut;
+            for (int j = 0; j < cnt; j++) {
+                P.batch_ev[off + j] = x;
+                P.batch_seg[off + j] = si;
+                x = P.p0[x];
+            }
+            P.lastord[tid] = cut;
+        }
+        total += tot_here;
+        __syncthreads();
+    }
+    if (tid == 0) { P.seg_start[P.nrounds] = total; P.scal[SC_BATCH] = total; }
+}
+
+// Consensus timestamp and sort key of each newly ordered event (swirld.py:295-306):
+// one warp per event, lane = famous witness.  For a witness that sees x the reference
+// walks down the witness's self-parent chain while the ancestor still sees x
+// (:298-302) and takes the timestamp of where it stops (the event before the first
+// seer, or the chain root -- quirk Q10); the lopsided median of :305 (quirk Q11).
+__global__ void __launch_bounds__(256) k_order_times(OrderParams P, int nbatch) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= nbatch) return;
+    const int M = P.M;
+    const int x = P.batch_ev[i], si = P.batch_seg[i];
+    const int c = P.creator[x];
+    const int nf = P.seg_nf[si];
+    double tv[2];
+    bool sees[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int k = lane + 32 * j;
+        tv[j] = 0.0; sees[j] = false;
+        if (k < nf) {
+            int a = P.seg_fw[(size_t)si * 64 + k];
+            if (P.row[(size_t)a * M + c] >= x) {
+                sees[j] = true;
+                while (P.row[(size_t)a * M + c] >= x && P.p0[a] >= 0) a = P.p0[a];
+                tv[j] = P.t[a];
+            }
+        }
+    }
+    const unsigned b0 = __ballot_sync(0xffffffffu, sees[0]), b1 = __ballot_sync(0xffffffffu, sees[1]);
+    const int n = __popc(b0) + __popc(b1);
+    // rank of my values among the n times (ties broken by position) -> sorted order
+    int rank[2] = {0, 0};
+#pragma unroll
+    for (int jj = 0; jj < 2; jj++)
+        for (int l = 0; l < 32; l++) {
+            const double o = __shfl_sync(0xffffffffu, tv[jj], l);
+            const bool os = ((jj ? b1 : b0) >> l) & 1;
+            if (!os) continue;
+            const int opos = jj * 32 + l;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int mypos = j * 32 + lane;
+                if (o < tv[j] || (o == tv[j] && opos < mypos)) rank[j]++;
+            }
+        }
+    const int ia = n / 2, ib = (n + 1) / 2;
+    if (ib >= n) { if (lane == 0) atomicMin(&P.scal[SC_ERR], -2); }   // IndexError, :305
+    double va = 0.0, vb = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const bool ha = sees[j] && rank[j] == ia, hb = sees[j] && rank[j] == ib;
+        const unsigned ma = __ballot_sync(0xffffffffu, ha), mb = __ballot_sync(0xffffffffu, hb);
+        if (ma) va = __shfl_sync(0xffffffffu, tv[j], __ffs(ma) - 1);
+        if (mb) vb = __shfl_sync(0xffffffffu, tv[j], __ffs(mb) - 1);
+    }
+    if (lane == 0) P.ts[i] = __dmul_rn(0.5, __dadd_rn(va, vb));
+    if (lane < 8) {     // key word `lane` = big-endian bytes 8*lane .. 8*lane+7 of white ^ sig(x)
+        u64 kw = 0;
+        for (int b = 0; b < 8; b++)
+            kw = (kw << 8) | (u64)(P.seg_white[(size_t)si * 64 + 8 * lane + b] ^ P.sig[(size_t)x * 64 + 8 * lane + b]);
+        P.key[(size_t)i * 8 + lane] = kw;
+    }
+}
+
+__device__ __forceinline__ bool order_less(const OrderParams &P, int a, int b) {
+    // a, b are batch slots (-1 = padding = +infinity); (ts, white ^ sig) ascending
+    // (swirld.py:306); the slot id is a last resort that never decides on distinct sigs
+    if (a < 0) return false;
+    if (b < 0) return true;
+    const double ta = P.ts[a], tb = P.ts[b];
+    if (ta < tb) return true;
+    if (ta > tb) return false;
+    for (int k = 0; k < 8; k++) {
+        const u64 ka = P.key[(size_t)a * 8 + k], kb = P.key[(size_t)b * 8 + k];
+        if (ka != kb) return ka < kb;
+    }
+    return a < b;
+}
+
+// One CTA per segment: bitonic sort of the segment's batch slots (padded to a power of
+// two with -1 = +infinity; P.perm holds 2 ints per batch slot so the padding is real),
+// then append to transactions / idx (swirld.py:306-309).
+__global__ void __launch_bounds__(1024) k_order_sort(OrderParams P) {
+    const int si = blockIdx.x;
+    const int s0 = P.seg_start[si], cnt = P.seg_start[si + 1] - s0;
+    if (cnt <= 0) return;
+    int n2 = 1;
+    while (n2 < cnt) n2 <<= 1;
+    int32_t *perm = P.perm + 2 * (size_t)s0;        // n2 < 2 * cnt
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) perm[i] = i < cnt ? s0 + i : -1;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int a = perm[i], b = perm[l];
+                    const bool up = (i & k) == 0;
+                    const bool sw = up ? order_less(P, b, a) : order_less(P, a, b);
+                    if (sw) { perm[i] = b; perm[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int x = P.batch_ev[perm[i]];
+        P.tx[P.tx_base + s0 + i] = x;
+        P.idx[x] = P.tx_base + s0 + i;
+    }
+}
+
+__global__ void k_fill_i32(int32_t *p, int32_t v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t st = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) p[i] = v;
+}
