@@ -61,6 +61,9 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
 void sw_destroy(sw_engine *e);
 /* Forget every event and all consensus state; keeps the allocations. */
 int sw_reset(sw_engine *e);
+/* Forget the consensus state (rounds, witnesses, fame, order) but keep the appended
+ * event columns resident on the device: the next sw_divide_rounds starts at 0 again. */
+int sw_rewind(sw_engine *e);
 const char *sw_last_error(const sw_engine *e);   /* e may be NULL: last create error */
 
 /* Node.add_event (swirld.py:114-120) for n events in arrival order, SoA columns:
@@ -104,6 +107,10 @@ int sw_sync(sw_engine *e);                     /* wait for the stream, fold timi
 int sw_stats(sw_engine *e, sw_stats_t *out);   /* implies sw_sync */
 /* Write >= bytes of device memory (evicts L2) on the engine's stream; for benchmarks. */
 int sw_flush_l2(sw_engine *e, int64_t bytes);
+/* CUDA events on the engine's stream, slots 0..15: record, and elapsed ms between two
+ * recorded slots (synchronises on the later one). */
+int sw_event_record(sw_engine *e, int slot);
+int sw_event_elapsed_ms(sw_engine *e, int slot_a, int slot_b, double *ms_out);
 
 int sw_version(void);
 

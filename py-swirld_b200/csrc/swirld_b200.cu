@@ -57,6 +57,7 @@ struct sw_engine {
     int32_t *h_scal = nullptr;    // pinned
     int32_t *h_newc = nullptr;    // pinned, Rcap
     cudaStream_t stream = nullptr;
+    cudaEvent_t user_ev[16] = {nullptr};
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> pool;
     sw_stats_t stats{};
@@ -123,7 +124,7 @@ int device_error(sw_engine *e) {     // after a sync: did a kernel flag an error
     return 0;
 }
 
-int reset_state(sw_engine *e) {
+int reset_state(sw_engine *e, bool keep_events = false) {
     const size_t RM = (size_t)e->Rcap * e->M;
     k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_W, -1, RM);
     CK(cudaMemsetAsync(e->d_famous, 0xff, RM, e->stream));
@@ -137,9 +138,12 @@ int reset_state(sw_engine *e) {
     CK(cudaMemcpyAsync(e->d_scal, sc, sizeof sc, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->stats.kernel_launches += 3;
-    e->n_events = e->n_divided = e->n_tx = 0;
-    std::fill(e->h_head.begin(), e->h_head.end(), -1);
-    std::fill(e->h_count.begin(), e->h_count.end(), 0);
+    e->n_divided = e->n_tx = 0;
+    if (!keep_events) {
+        e->n_events = 0;
+        std::fill(e->h_head.begin(), e->h_head.end(), -1);
+        std::fill(e->h_count.begin(), e->h_count.end(), 0);
+    }
     memset(e->h_scal, 0, sizeof(int32_t) * SC_COUNT);
     return 0;
 }
@@ -225,6 +229,7 @@ void sw_destroy(sw_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     fold_spans(e);
     for (auto ev : e->pool) cudaEventDestroy(ev);
+    for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
     void *ptrs[] = {e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_V, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
@@ -246,6 +251,33 @@ int sw_reset(sw_engine *e) {
     int rc = reset_state(e);
     memset(&e->stats, 0, sizeof e->stats);
     return rc;
+}
+
+int sw_rewind(sw_engine *e) {
+    if (!e) return SW_E_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    fold_spans(e);
+    return reset_state(e, true);
+}
+
+int sw_event_record(sw_engine *e, int slot) {
+    if (!e || slot < 0 || slot >= 16) return fail(e, SW_E_ARG, "bad event slot");
+    CK(cudaSetDevice(e->device));
+    if (!e->user_ev[slot]) CK(cudaEventCreate(&e->user_ev[slot]));
+    CK(cudaEventRecord(e->user_ev[slot], e->stream));
+    return SW_OK;
+}
+
+int sw_event_elapsed_ms(sw_engine *e, int a, int b, double *ms_out) {
+    if (!e || a < 0 || a >= 16 || b < 0 || b >= 16 || !ms_out || !e->user_ev[a] || !e->user_ev[b])
+        return fail(e, SW_E_ARG, "bad event slot");
+    CK(cudaSetDevice(e->device));
+    CK(cudaEventSynchronize(e->user_ev[b]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e->user_ev[a], e->user_ev[b]));
+    *ms_out = ms;
+    return SW_OK;
 }
 
 int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const int32_t *creator,

@@ -19,7 +19,7 @@ SW_E = {-1: "SW_E_ARG", -2: "SW_E_INDEX", -3: "SW_E_KEY", -4: "SW_E_CUDA", -5: "
 
 # every symbol include/swirld_b200.h declares (tests check the library exports them all)
 SYMBOLS = [
-    "sw_create", "sw_destroy", "sw_reset", "sw_last_error", "sw_append", "sw_divide_rounds",
+    "sw_create", "sw_destroy", "sw_reset", "sw_rewind", "sw_event_record", "sw_event_elapsed_ms", "sw_last_error", "sw_append", "sw_divide_rounds",
     "sw_decide_fame", "sw_find_order", "sw_n_events", "sw_n_divided", "sw_max_round",
     "sw_n_transactions", "sw_get_round", "sw_get_witness_flags", "sw_get_famous", "sw_get_can_see",
     "sw_get_witness_table", "sw_get_consensus", "sw_get_transactions", "sw_get_idx", "sw_get_height",
@@ -61,6 +61,9 @@ def load_library(path: str = LIB_PATH):
     L.sw_create.argtypes = [i32, i32, P(C.c_int64), i32, i32, P(vp)]
     L.sw_destroy.argtypes = [vp]; L.sw_destroy.restype = None
     L.sw_reset.argtypes = [vp]
+    L.sw_rewind.argtypes = [vp]
+    L.sw_event_record.argtypes = [vp, i32]
+    L.sw_event_elapsed_ms.argtypes = [vp, i32, i32, P(C.c_double)]
     L.sw_last_error.argtypes = [vp]; L.sw_last_error.restype = C.c_char_p
     L.sw_append.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.sw_divide_rounds.argtypes = [vp, i32, i32]
@@ -123,6 +126,17 @@ class Engine:
 
     def reset(self):
         self._chk(self._lib.sw_reset(self._h))
+
+    def rewind(self):
+        self._chk(self._lib.sw_rewind(self._h))
+
+    def record(self, slot):
+        self._chk(self._lib.sw_event_record(self._h, slot))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_double()
+        self._chk(self._lib.sw_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
 
     # -- the path
     def append(self, p0, p1, creator, t, sig):
