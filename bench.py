@@ -175,6 +175,26 @@ def workload_config(wl, world):
                   "(can_see + T tables) also exceeds L2 at c3"}
 
 
+# --------------------------------------------------------------------------- multi-rank plumbing
+def rank_seed(rank):
+    """Every rank advances its own node-view: an independent trace."""
+    return 1 + rank
+
+
+def max_over_ranks(values, dist, device):
+    """Element-wise max of a few per-rank timings (the job is as slow as its slowest rank)."""
+    import torch
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def whole_job_rate(world, events_per_rank_step, steps, ms_max):
+    """events/s of the whole job: all ranks' events over the slowest rank's time."""
+    return world * events_per_rank_step * steps / (ms_max * 1e-3)
+
+
 # --------------------------------------------------------------------------- GPU arm
 def bench_ours(args, wl, rank, world, local_rank):
     import torch
@@ -194,7 +214,7 @@ def bench_ours(args, wl, rank, world, local_rank):
         torch.cuda.synchronize()
 
     M, N, K = wl["M"], wl["N"], wl["K"]
-    tr = make_trace(wl, 1 + rank)
+    tr = make_trace(wl, rank_seed(rank))
     # pinned host copies of the event columns (the e2e leg's source)
     pin = {}
     for k in ("p0", "p1", "creator", "t", "sig"):
@@ -276,10 +296,7 @@ def bench_ours(args, wl, rank, world, local_rank):
         e2e_ms += step_e2e()
     barrier()
 
-    t_dev = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, wall_ms_max = [float(x) for x in t_dev.tolist()]
+    dev_ms_max, e2e_ms_max, wall_ms_max = max_over_ranks([dev_ms, e2e_ms, wall_ms], dist, "cuda")
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -291,8 +308,8 @@ def bench_ours(args, wl, rank, world, local_rank):
         # k_divide + k_strong are bracketed together by ms_divide_rounds; k_strong is the
         # small witness-only pass (see profiles/ for the split)
         achieved = (N * args.steps * bpe) / (ms_div * 1e-3) / 1e9
-        value = world * N * args.steps / (dev_ms_max * 1e-3)
-        e2e_value = world * N * e2e_steps / (e2e_ms_max * 1e-3)
+        value = whole_job_rate(world, N, args.steps, dev_ms_max)
+        e2e_value = whole_job_rate(world, N, e2e_steps, e2e_ms_max)
         # CPU baseline next to it: one pass of the oracle port on the box's host cores
         n_cpu, s_cpu, fo_cpu = run_cpu_pass(tr, K, limit=None if N <= 1000000 else 1000000)
         line = {

@@ -45,7 +45,7 @@ def load_reference():
 
 def run_reference(tr, K: int, stake=None, snapshots: bool = False):
     """Feed trace `tr` (swirld_b200.traces.Trace) to the reference in chunks of
-    K events.  Returns a dict of numpy arrays in index space plus timings.
+    K events (K may also be an explicit list of chunk sizes).  Returns a dict of numpy arrays in index space plus timings.
 
     famous: int8[N]  -1 = no entry in Node.famous, 0 = False, 1 = True
     witness: uint8[N] 1 iff the event is a value of Node.witnesses[r] for some r
@@ -75,8 +75,9 @@ def run_reference(tr, K: int, stake=None, snapshots: bool = False):
     snaps = []
     sink = io.StringIO()
     first = 0
+    sizes = iter(K) if isinstance(K, (list, tuple)) else None
     while first < N:
-        cnt = min(K, N - first)
+        cnt = min(next(sizes) if sizes is not None else K, N - first)
         ids = list(range(first, first + cnt))
         for i in ids:
             par = () if p0[i] < 0 else (p0[i], p1[i])
