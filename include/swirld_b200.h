@@ -112,6 +112,11 @@ int sw_flush_l2(sw_engine *e, int64_t bytes);
 int sw_event_record(sw_engine *e, int slot);
 int sw_event_elapsed_ms(sw_engine *e, int slot_a, int slot_b, double *ms_out);
 
+/* Profiling aid: 16 cycle counters of the level walker (compute role [0..7]: process,
+ * level-barrier, batch-barrier cycles, events, levels, batches; prepare role [8..15]:
+ * stream, prepare, cp.async-wait, batch-barrier cycles). */
+int sw_debug_counters(sw_engine *e, int64_t *out16, int clear);
+
 int sw_version(void);
 
 #ifdef __cplusplus

@@ -4,6 +4,10 @@
 // on append (what Node.is_valid_event checks, swirld.py:104-108), keeps the
 // creator/height/chain-position mirrors it needs for that, and moves bytes.
 #include "swirld_kernels.cuh"
+#include "swirld_divide.cuh"
+#include "swirld_levels.cuh"
+
+#include <cstdlib>
 #include "../../include/swirld_b200.h"
 
 #include <algorithm>
@@ -30,7 +34,11 @@ struct sw_engine {
     std::vector<int32_t> h_creator, h_height, h_head, h_count, h_seq_stage;
     int n_events = 0, n_divided = 0, n_tx = 0;
     // device columns
-    int32_t *d_p0 = nullptr, *d_p1 = nullptr, *d_creator = nullptr, *d_seq = nullptr;
+    int32_t *d_p0 = nullptr, *d_p1 = nullptr, *d_creator = nullptr, *d_seq = nullptr, *d_height = nullptr;
+    int32_t *d_hist = nullptr, *d_cursor = nullptr, *d_order = nullptr, *d_gpos = nullptr, *d_lvl_start = nullptr;
+    GDesc *d_gdesc = nullptr;
+    long long *d_dbg = nullptr;
+    int divide_impl = 4;          // 4 = level-scheduled (default), 3 = per-event flags
     double *d_t = nullptr;
     uint8_t *d_sig = nullptr;
     int32_t *d_row = nullptr, *d_round = nullptr;
@@ -148,17 +156,45 @@ int reset_state(sw_engine *e, bool keep_events = false) {
     return 0;
 }
 
-template <int NC>
+template <int NC, bool UNIT>
 int launch_divide(sw_engine *e, const DivParams &P) {
-    static bool attr_set[2] = {false, false};
     const size_t smem = sizeof(DivSmem<NC>);
-    if (!attr_set[NC - 1]) {
-        CK(cudaFuncSetAttribute(k_divide<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[NC - 1] = true;
-    }
-    k_divide<NC><<<1, 1024, smem, e->stream>>>(P);
+    CK(cudaFuncSetAttribute(k_divide<NC, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_divide<NC, UNIT><<<1, 1024, smem, e->stream>>>(P);
     CK(cudaGetLastError());
     return 0;
+}
+
+template <int NC, bool UNIT>
+int launch_levels(sw_engine *e, const Div4Params &Q) {
+    const size_t smem = sizeof(LvSmem<NC>);
+    CK(cudaFuncSetAttribute(k_divide_levels<NC, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_divide_levels<NC, UNIT><<<1, LV_THREADS, smem, e->stream>>>(Q);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// counting sort of the chunk by height, then the level-scheduled walk
+int divide_levels(sw_engine *e, const DivParams &P) {
+    int hmin = e->h_height[P.first], hmax = hmin;
+    for (int i = P.first; i < P.first + P.n; i++) { hmin = std::min(hmin, e->h_height[i]); hmax = std::max(hmax, e->h_height[i]); }
+    LvlParams L{};
+    L.first = P.first; L.n = P.n; L.hmin = hmin; L.nbins = hmax - hmin + 1;
+    L.height = e->d_height; L.p0 = e->d_p0; L.p1 = e->d_p1; L.creator = e->d_creator;
+    L.hist = e->d_hist; L.cursor = e->d_cursor; L.order = e->d_order; L.gpos = e->d_gpos;
+    L.lvl_start = e->d_lvl_start; L.scal = e->d_scal; L.gdesc = e->d_gdesc;
+    CK(cudaMemsetAsync(e->d_hist, 0, sizeof(int32_t) * (size_t)L.nbins, e->stream));
+    const int blocks = std::max(1, std::min(296, (P.n + 255) / 256));
+    k_lvl_hist<<<blocks, 256, 0, e->stream>>>(L);
+    k_lvl_scan<<<1, 1024, 0, e->stream>>>(L);
+    k_lvl_scatter<<<blocks, 256, 0, e->stream>>>(L);
+    k_lvl_desc<<<blocks, 256, 0, e->stream>>>(L);
+    CK(cudaGetLastError());
+    Div4Params Q{};
+    Q.d = P; Q.gdesc = e->d_gdesc; Q.lvl_start = e->d_lvl_start;
+    e->stats.kernel_launches += 4;
+    if (e->NC == 1) return e->unit ? launch_levels<1, true>(e, Q) : launch_levels<1, false>(e, Q);
+    return e->unit ? launch_levels<2, true>(e, Q) : launch_levels<2, false>(e, Q);
 }
 
 }  // namespace
@@ -193,6 +229,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
     i64 per = std::min<i64>(M, (2 * e->tot) / 3 + 1);
     if (per < 1) per = 1;
     e->Rcap = (int)std::min<i64>((i64)e->cap + 2, (i64)e->cap / per + 16);
+    if (const char *impl = getenv("SW_DIVIDE_IMPL")) e->divide_impl = atoi(impl) == 3 ? 3 : 4;
     e->h_head.assign(M, -1);
     e->h_count.assign(M, 0);
     e->h_creator.reserve(e->cap);
@@ -202,7 +239,10 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         const size_t cap = e->cap, RM = (size_t)e->Rcap * M;
         CK(dalloc(&e->d_p0, cap)); CK(dalloc(&e->d_p1, cap)); CK(dalloc(&e->d_creator, cap)); CK(dalloc(&e->d_seq, cap));
-        CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64));
+        CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64)); CK(dalloc(&e->d_height, cap));
+        CK(dalloc(&e->d_hist, cap + 2)); CK(dalloc(&e->d_cursor, cap + 2)); CK(dalloc(&e->d_order, cap));
+        CK(dalloc(&e->d_gpos, cap)); CK(dalloc(&e->d_lvl_start, cap + 2)); CK(dalloc(&e->d_gdesc, cap));
+        CK(dalloc(&e->d_dbg, (size_t)16)); CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 16, e->stream));
         CK(dalloc(&e->d_row, cap * M)); CK(dalloc(&e->d_T, cap * M)); CK(dalloc(&e->d_SM, cap));
         CK(dalloc(&e->d_round, cap)); CK(dalloc(&e->d_wit, cap)); CK(dalloc(&e->d_famous_ev, cap));
         CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_S, RM)); CK(dalloc(&e->d_V, RM)); CK(dalloc(&e->d_famous, RM));
@@ -230,7 +270,8 @@ void sw_destroy(sw_engine *e) {
     fold_spans(e);
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
-    void *ptrs[] = {e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
+    void *ptrs[] = {e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
+                    e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_V, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
                     e->d_batch_ev, e->d_batch_seg, e->d_perm, e->d_ts, e->d_key, e->d_seg_start, e->d_seg_fw,
@@ -321,9 +362,10 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
     CK(cudaMemcpyAsync(e->d_t + base, t, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->d_sig + (size_t)base * 64, sig, (size_t)64 * n, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->d_seq + base, e->h_seq_stage.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_height + base, e->h_height.data() + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     // h_seq_stage is reused by the next append: the copy above must have left the host buffer
     CK(cudaStreamSynchronize(e->stream));
-    e->stats.h2d_bytes += (i64)n * (4 * 4 + 8 + 64);
+    e->stats.h2d_bytes += (i64)n * (5 * 4 + 8 + 64);
     e->stats.events += n;
     e->n_events += n;
     return SW_OK;
@@ -339,13 +381,16 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     P.M = e->M; P.first = first; P.n = n; P.Rcap = e->Rcap;
     P.p0 = e->d_p0; P.p1 = e->d_p1; P.creator = e->d_creator;
     P.row = e->d_row; P.T = e->d_T; P.SM = e->d_SM; P.round = e->d_round; P.wit = e->d_wit; P.W = e->d_W;
-    P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.scal = e->d_scal;
+    P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.scal = e->d_scal; P.dbg = e->d_dbg;
     StrongParams Q{};
     Q.M = e->M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
     Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
     {
         Span sp(e, 0);
-        int rc = e->NC == 1 ? launch_divide<1>(e, P) : launch_divide<2>(e, P);
+        int rc;
+        if (e->divide_impl == 4) rc = divide_levels(e, P);
+        else rc = e->NC == 1 ? (e->unit ? launch_divide<1, true>(e, P) : launch_divide<1, false>(e, P))
+                             : (e->unit ? launch_divide<2, true>(e, P) : launch_divide<2, false>(e, P));
         if (rc < 0) return rc;
         const int wpb = 8, blocks = (n + wpb - 1) / wpb;
         if (e->NC == 1) k_strong<1><<<blocks, wpb * 32, 0, e->stream>>>(Q);
@@ -509,6 +554,15 @@ int sw_get_consensus(sw_engine *e, int32_t *out, int cap) {
     for (int r = 0; r <= mr; r++)
         if (flags[r]) { if (cnt < cap) out[cnt] = r; cnt++; }
     return cnt;
+}
+
+int sw_debug_counters(sw_engine *e, int64_t *out16, int clear) {
+    if (!e || !out16) return SW_E_ARG;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out16, e->d_dbg, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+    if (clear) CK(cudaMemset(e->d_dbg, 0, sizeof(long long) * 16));
+    return SW_OK;
 }
 
 int sw_flush_l2(sw_engine *e, int64_t bytes) {

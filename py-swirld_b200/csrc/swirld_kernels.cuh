@@ -22,8 +22,6 @@
 typedef unsigned long long u64;
 typedef long long i64;
 
-#define SW_RING 256          // events whose row/T/round stay in shared memory
-#define SW_RING_WINS (SW_RING / 32)
 #define SW_WC 16             // rounds of the witness table cached in shared memory
 
 enum { SC_MAX_ROUND = 0, SC_ERR = 1, SC_NEWC = 2, SC_BATCH = 3, SC_NSEG = 4, SC_COUNT = 8 };
@@ -41,20 +39,10 @@ struct DivParams {
     i64 tot2;            // 2 * total stake
     int unit;            // all stakes == 1
     int32_t *scal;       // SC_*
+    long long *dbg;      // 16 cycle counters for profiling builds of the walker, may be NULL
 };
 
 // ---------------------------------------------------------------- small helpers
-__device__ __forceinline__ unsigned ld_acquire_shared(const unsigned *p) {
-    unsigned v;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_shared(unsigned *p, unsigned v) {
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
-}
-
 __device__ __forceinline__ i64 wsum(u64 m, int unit, const i64 *stake_s) {
     if (unit) return (i64)__popcll(m);
     i64 s = 0;
@@ -64,145 +52,6 @@ __device__ __forceinline__ i64 wsum(u64 m, int unit, const i64 *stake_s) {
         m &= m - 1;
     }
     return s;
-}
-
-template <int NC>
-struct DivSmem {
-    int32_t row[SW_RING][NC * 32];
-    u64 T[SW_RING][NC * 32];
-    int32_t round[SW_RING];
-    unsigned done[SW_RING];
-    int32_t Wc[SW_WC][NC * 32];
-    i64 stake[NC * 32];
-    int rmaxp[2];
-};
-
-// ---------------------------------------------------------------- K1+K2: divide_rounds
-// One CTA of 32 warps walks the events [first, first+n) in windows of 32 consecutive
-// indices, one warp per event, lane = member column (NC columns per lane).  Inside a
-// window a warp spins on its parents' per-event "done" flags in shared memory (acquire /
-// release at CTA scope); dependencies always point to lower indices, so the window always
-// drains.  The last SW_RING events' rows, T matrices and rounds live in a shared-memory
-// ring (parents are almost always recent heads); older parents come from L2/HBM.
-template <int NC>
-__global__ void __launch_bounds__(1024, 1) k_divide(DivParams P) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    DivSmem<NC> &S = *reinterpret_cast<DivSmem<NC> *>(smraw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = P.M;
-    constexpr int MS = NC * 32;
-
-    for (int i = tid; i < SW_RING; i += 1024) S.done[i] = 0;
-    if (tid < MS) S.stake[tid] = tid < M ? P.stake[tid] : 0;
-    int rmax = P.scal[SC_MAX_ROUND];
-    int wbase = max(0, rmax - (SW_WC / 2 - 1));
-    if (tid < 2) S.rmaxp[tid] = rmax;
-    for (int i = tid; i < SW_WC * MS; i += 1024) {
-        int slot = i / MS, c = i % MS;
-        int r = wbase + ((slot - (wbase % SW_WC) + SW_WC) % SW_WC);
-        S.Wc[slot][c] = (c < M && r < P.Rcap) ? P.W[(size_t)r * M + c] : -1;
-    }
-    __syncthreads();
-
-    const int w_first = P.first >> 5, w_last = (P.first + P.n - 1) >> 5;
-    for (int win = w_first; win <= w_last; ++win) {
-        const int h = win * 32 + warp;
-        if (h >= P.first && h < P.first + P.n) {
-            const int pa = __ldg(P.p0 + h), pb = __ldg(P.p1 + h), cr = __ldg(P.creator + h);
-            int rowh[NC];
-            u64 t[NC];
-            int r, ra = -1;
-            bool promoted;
-            if (pa < 0) {                       // root (swirld.py:195-198)
-#pragma unroll
-                for (int j = 0; j < NC; j++) { rowh[j] = -1; t[j] = 0; }
-                r = -1; promoted = true;        // round 0, own term only
-            } else {
-                const bool a_sm = pa >= P.first && (win - (pa >> 5)) < SW_RING_WINS;
-                const bool b_sm = pb >= P.first && (win - (pb >> 5)) < SW_RING_WINS;
-                const int sa = pa & (SW_RING - 1), sb = pb & (SW_RING - 1);
-                if (a_sm && (pa >> 5) == win)
-                    while (ld_acquire_shared(&S.done[sa]) != (unsigned)(pa + 1)) { }
-                if (b_sm && (pb >> 5) == win)
-                    while (ld_acquire_shared(&S.done[sb]) != (unsigned)(pb + 1)) { }
-                ra = a_sm ? S.round[sa] : __ldcg(P.round + pa);
-                const int rb = b_sm ? S.round[sb] : __ldcg(P.round + pb);
-                r = max(ra, rb);                                        // swirld.py:200
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const int c = lane + 32 * j;
-                    int va = -1, vb = -1;
-                    u64 ta = 0, tb = 0;
-                    if (c < M) {
-                        va = a_sm ? S.row[sa][c] : __ldcg(P.row + (size_t)pa * M + c);
-                        vb = b_sm ? S.row[sb][c] : __ldcg(P.row + (size_t)pb * M + c);
-                        if (ra == r) ta = a_sm ? S.T[sa][c] : __ldcg(P.T + (size_t)pa * M + c);
-                        if (rb == r) tb = b_sm ? S.T[sb][c] : __ldcg(P.T + (size_t)pb * M + c);
-                    }
-                    rowh[j] = max(va, vb);                              // swirld.py:203-205
-                    t[j] = ta | tb;
-                }
-                int cnt = 0;
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const i64 hits = wsum(t[j], P.unit, S.stake);       // swirld.py:209-214
-                    cnt += __popc(__ballot_sync(0xffffffffu, 3 * hits > P.tot2));
-                }
-                promoted = 3 * (i64)cnt > P.tot2;                       // swirld.py:216
-            }
-            int rh = r + (promoted ? 1 : 0);                            // swirld.py:217-219
-            const bool wit = (pa < 0) || rh > ra;                       // swirld.py:221 / 196-197
-            if (rh >= P.Rcap) { if (lane == 0) atomicMin(&P.scal[SC_ERR], -5); rh = P.Rcap - 1; }
-            const bool w_sm = rh >= wbase && rh < wbase + SW_WC;
-            if (wit && lane == 0) {                                      // swirld.py:222
-                P.W[(size_t)rh * M + cr] = h;
-                if (w_sm) S.Wc[rh % SW_WC][cr] = h;
-                atomicMax(&S.rmaxp[win & 1], rh);
-            }
-            __syncwarp();
-            u64 smask = 0;
-#pragma unroll
-            for (int j = 0; j < NC; j++) {
-                const int c = lane + 32 * j;
-                if (c == cr) rowh[j] = h;                                // swirld.py:220
-                int w = -1;
-                if (c < M) w = w_sm ? S.Wc[rh % SW_WC][c] : __ldcg(P.W + (size_t)rh * M + c);
-                const bool sm = (c < M) && w >= 0 && rowh[j] >= w;
-                smask |= (u64)__ballot_sync(0xffffffffu, sm) << (32 * j);
-                const u64 th = (promoted ? 0ull : t[j]) | (sm ? (1ull << cr) : 0ull);
-                if (c < M) {
-                    const int sh = h & (SW_RING - 1);
-                    S.row[sh][c] = rowh[j];
-                    S.T[sh][c] = th;
-                    P.row[(size_t)h * M + c] = rowh[j];
-                    P.T[(size_t)h * M + c] = th;
-                }
-            }
-            if (lane == 0) {
-                S.round[h & (SW_RING - 1)] = rh;
-                P.round[h] = rh;
-                P.wit[h] = wit ? 1 : 0;
-                P.SM[h] = smask;
-            }
-            __syncwarp();
-            if (lane == 0) st_release_shared(&S.done[h & (SW_RING - 1)], (unsigned)(h + 1));
-        }
-        __syncthreads();
-        rmax = max(rmax, S.rmaxp[win & 1]);
-        const int nb = max(wbase, rmax - (SW_WC / 2 - 1));
-        if (nb != wbase) {                      // uniform: every thread sees the same rmax
-            for (int i = tid; i < SW_WC * MS; i += 1024) {
-                int slot = i / MS, c = i % MS;
-                int ro = wbase + ((slot - (wbase % SW_WC) + SW_WC) % SW_WC);
-                int rn = nb + ((slot - (nb % SW_WC) + SW_WC) % SW_WC);
-                if (rn != ro)
-                    S.Wc[slot][c] = (c < M && rn < P.Rcap) ? __ldcg(P.W + (size_t)rn * M + c) : -1;
-            }
-            wbase = nb;
-            __syncthreads();
-        }
-    }
-    if (tid == 0) P.scal[SC_MAX_ROUND] = rmax;
 }
 
 // ---------------------------------------------------------------- K3-prep: strongly-seen sets

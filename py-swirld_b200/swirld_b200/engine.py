@@ -23,7 +23,7 @@ SYMBOLS = [
     "sw_decide_fame", "sw_find_order", "sw_n_events", "sw_n_divided", "sw_max_round",
     "sw_n_transactions", "sw_get_round", "sw_get_witness_flags", "sw_get_famous", "sw_get_can_see",
     "sw_get_witness_table", "sw_get_consensus", "sw_get_transactions", "sw_get_idx", "sw_get_height",
-    "sw_sync", "sw_stats", "sw_flush_l2", "sw_version",
+    "sw_sync", "sw_stats", "sw_flush_l2", "sw_version", "sw_debug_counters",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library(path: str = LIB_PATH):
     L.sw_stats.argtypes = [vp, P(SwStats)]
     L.sw_flush_l2.argtypes = [vp, i64]
     L.sw_version.argtypes = []
+    L.sw_debug_counters.argtypes = [vp, vp, i32]
     _lib = L
     return L
 
@@ -235,6 +236,11 @@ class Engine:
         s = SwStats()
         self._chk(self._lib.sw_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def debug_counters(self, clear=True):
+        out = np.zeros(16, np.int64)
+        self._chk(self._lib.sw_debug_counters(self._h, _ptr(out), 1 if clear else 0))
+        return out
 
     def flush_l2(self, nbytes=256 << 20):
         self._chk(self._lib.sw_flush_l2(self._h, nbytes))
