@@ -459,7 +459,7 @@ int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
     P.ts = e->d_ts; P.key = e->d_key; P.perm = e->d_perm; P.tx = e->d_tx; P.idx = e->d_idx; P.tx_base = e->n_tx; P.scal = e->d_scal;
     cudaEvent_t a = get_event(e), b = get_event(e);
     cudaEventRecord(a, e->stream);
-    k_order_plan<<<1, 64, 0, e->stream>>>(P);
+    k_order_plan<<<1, 1024, 0, e->stream>>>(P);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));      // rs (host vector) was consumed by the copy above

@@ -133,12 +133,13 @@ struct FameParams {
 };
 
 __global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
-    __shared__ u64 sv[64];
-    __shared__ i64 vsum[64];
+    // voter rows are double-buffered: the row of round r_+1 is fetched while r_ votes
+    __shared__ u64 sv[2][64];
+    __shared__ i64 vsum[2][64];
     __shared__ i64 stake_s[64];
-    __shared__ int vw[64];
-    __shared__ int vcoin[64];
-    __shared__ int s_maxc, s_lo;
+    __shared__ int vw[2][64];
+    __shared__ int vcoin[2][64];
+    __shared__ int s_maxc, s_lo2[2];
     const int tid = threadIdx.x, M = P.M;
     const int max_r = P.scal[SC_MAX_ROUND];                     // swirld.py:225
     if (tid < 64) stake_s[tid] = tid < M ? P.stake[tid] : 0;
@@ -159,59 +160,86 @@ __global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
                 if (P.W[(size_t)r * M + m] >= 0 && P.famous[(size_t)r * M + m] < 0) cnt++;
         P.rem[r] = cnt;
     }
-    if (tid == 0) s_lo = max_c;
+    auto load_voters = [&](int r_, int buf) {                   // threads 0..63
+        const int w = (tid < M && r_ <= max_r) ? P.W[(size_t)r_ * M + tid] : -1;
+        vw[buf][tid] = w;
+        const u64 s = w >= 0 ? P.S[(size_t)r_ * M + tid] : 0ull;
+        sv[buf][tid] = s;
+        vcoin[buf][tid] = w >= 0 ? (P.sig[(size_t)w * 64] >> 7) : 0;   // swirld.py:272
+        vsum[buf][tid] = wsum(s, P.unit, stake_s);
+    };
+    if (tid < 2) s_lo2[tid] = max_c;
+    if (tid < 64) load_voters(max_c + 1, (max_c + 1) & 1);
     __syncthreads();
+    // 4 threads share one undecided witness (r, mx); each covers a quarter of the voters
+    const int q = tid & 3, mq0 = q * 16;
+    const unsigned qmask = 0xFu << (threadIdx.x & 28);
     for (int r_ = max_c + 1; r_ <= max_r; ++r_) {               // iter_voters, swirld.py:238-241
-        if (tid < 64) {
-            int w = tid < M ? P.W[(size_t)r_ * M + tid] : -1;
-            vw[tid] = w;
-            u64 s = w >= 0 ? P.S[(size_t)r_ * M + tid] : 0ull;
-            sv[tid] = s;
-            vcoin[tid] = w >= 0 ? (P.sig[(size_t)w * 64] >> 7) : 0;  // swirld.py:272
-            vsum[tid] = wsum(s, P.unit, stake_s);
+        const int buf = r_ & 1;
+        if (tid < 64) load_voters(r_ + 1, buf ^ 1);             // prefetch the next round's voters
+        // first round that may still hold an undecided witness.  The value used now was
+        // computed during the previous iteration (so it may lag: a harmless superset); the
+        // next one is computed here while this round votes.
+        const int lo = s_lo2[buf];
+        if (tid == 64) {
+            int nlo = lo;
+            while (nlo < r_ && P.rem[nlo] == 0) nlo++;
+            s_lo2[buf ^ 1] = nlo;
         }
-        if (tid == 0) {
-            int lo = s_lo;
-            while (lo < r_ && P.rem[lo] == 0) lo++;
-            s_lo = lo;
-        }
-        __syncthreads();
-        const int lo = s_lo;
         const int nslots = (r_ - lo) * M;
-        for (int i = tid; i < nslots; i += 1024) {              // iter_undetermined, :231-236
-            const int r = lo + i / M, mx = i % M;
-            if (P.consensus[r]) continue;
-            const size_t slot = (size_t)r * M + mx;
-            const int x = P.W[slot];
-            if (x < 0 || P.famous[slot] >= 0) continue;
+        for (int base = 0; base < nslots; base += 256) {        // iter_undetermined, :231-236
+            const int i = base + (tid >> 2);
+            bool live = i < nslots;
+            int r = 0, mx = 0, x = -1;
+            size_t slot = 0;
+            u64 pv = 0;
+            if (live) {         // four independent loads (one memory latency, not a chain of four)
+                r = lo + i / M; mx = i % M;
+                slot = (size_t)r * M + mx;
+                const int cons = P.consensus[r];
+                x = P.W[slot];
+                const int fam = P.famous[slot];
+                pv = P.V[slot];
+                live = !cons && x >= 0 && fam < 0;
+            }
             const int d = r_ - r;
-            const u64 prev = d > 1 ? P.V[slot] : 0ull;
+            const u64 prev = d > 1 ? pv : 0ull;
             const bool coin_round = (d % P.C) == 0;
             u64 mask = 0;
             int decided = -1;
-            for (int m = 0; m < M; m++) {
-                if (vw[m] < 0) continue;
-                const u64 s = sv[m];
-                int vote;
-                if (d == 1) vote = (int)((s >> mx) & 1);         // swirld.py:256-257
-                else {
-                    const i64 yes = wsum(s & prev, P.unit, stake_s);   // majority, :20-27
-                    const i64 no = vsum[m] - yes;
-                    const int v = no > yes ? 0 : 1;
-                    const i64 tt = no > yes ? no : yes;
-                    if (!coin_round) {
-                        if (3 * tt > P.tot2) { if (decided < 0) decided = v; continue; }  // :261-263
-                        vote = v;                                 // :265
-                    } else vote = (3 * tt > P.tot2) ? v : vcoin[m];   // :267-272
+            if (live) {
+                for (int m = mq0; m < mq0 + 16 && m < M; m++) {
+                    if (vw[buf][m] < 0) continue;
+                    const u64 s = sv[buf][m];
+                    int vote;
+                    if (d == 1) vote = (int)((s >> mx) & 1);         // swirld.py:256-257
+                    else {
+                        const i64 yes = wsum(s & prev, P.unit, stake_s);   // majority, :20-27
+                        const i64 no = vsum[buf][m] - yes;
+                        const int v = no > yes ? 0 : 1;
+                        const i64 tt = no > yes ? no : yes;
+                        if (!coin_round) {
+                            if (3 * tt > P.tot2) { if (decided < 0) decided = v; continue; }  // :261-263
+                            vote = v;                                 // :265
+                        } else vote = (3 * tt > P.tot2) ? v : vcoin[buf][m];   // :267-272
+                    }
+                    mask |= (u64)vote << m;
                 }
-                mask |= (u64)vote << m;
             }
-            if (decided >= 0) {
-                P.famous[slot] = (int8_t)decided;
-                P.famous_ev[x] = (int8_t)decided;
-                P.done[r] = 1;
-                atomicSub(&P.rem[r], 1);
-            } else P.V[slot] = mask;
+            // combine the four quarters (all deciders agree on the value)
+            unsigned mlo = (unsigned)mask, mhi = (unsigned)(mask >> 32);
+            mlo |= __shfl_xor_sync(qmask, mlo, 1); mhi |= __shfl_xor_sync(qmask, mhi, 1);
+            mlo |= __shfl_xor_sync(qmask, mlo, 2); mhi |= __shfl_xor_sync(qmask, mhi, 2);
+            decided = max(decided, __shfl_xor_sync(qmask, decided, 1));
+            decided = max(decided, __shfl_xor_sync(qmask, decided, 2));
+            if (live && q == 0) {
+                if (decided >= 0) {
+                    P.famous[slot] = (int8_t)decided;
+                    P.famous_ev[x] = (int8_t)decided;
+                    P.done[r] = 1;
+                    atomicSub(&P.rem[r], 1);
+                } else P.V[slot] = ((u64)mhi << 32) | mlo;
+            }
         }
         __syncthreads();
     }
@@ -258,60 +286,87 @@ struct OrderParams {
 // exactly the not-yet-ordered events x with x <= max_{w in f_w & tbd} row(w)[c], and
 // "received" (swirld.py:291-293) is monotone along the chain, so the newly ordered
 // events of chain c are (lastord[c], min(reach, received-threshold)].
-__global__ void __launch_bounds__(64, 1) k_order_plan(OrderParams P) {
+__global__ void __launch_bounds__(1024, 1) k_order_plan(OrderParams P) {
     __shared__ int fw[64];
     __shared__ int cnts[64];
     __shared__ int nf_s;
+    __shared__ unsigned ball[2];
+    __shared__ int mat[64][64];          // mat[i][c] = row(fw[i])[c]
+    __shared__ i64 st[64];               // stake of fw[i]'s creator
+    __shared__ int tbd_s[64];            // fw[i] not yet ordered
+    __shared__ int U_s[64], thr_s[64];
     const int tid = threadIdx.x, M = P.M;
     int total = 0;
     for (int si = 0; si < P.nrounds; ++si) {
         const int r = P.rounds[si];
-        int w = -1, fam = -1;
-        if (tid < M && r >= 0 && r < P.Rcap) { w = P.W[(size_t)r * M + tid]; fam = P.famous[(size_t)r * M + tid]; }
-        if (w >= 0 && fam < 0) atomicMin(&P.scal[SC_ERR], -3);   // self.famous[w] KeyError, :284
-        const bool isf = w >= 0 && fam == 1;
-        const unsigned b0 = __ballot_sync(0xffffffffu, isf);
-        __shared__ unsigned ball[2];
-        if ((tid & 31) == 0) ball[tid >> 5] = b0;
+        if (tid < 64) {
+            int w = -1, fam = -1;
+            if (tid < M && r >= 0 && r < P.Rcap) { w = P.W[(size_t)r * M + tid]; fam = P.famous[(size_t)r * M + tid]; }
+            if (w >= 0 && fam < 0) atomicMin(&P.scal[SC_ERR], -3);   // self.famous[w] KeyError, :284
+            const bool isf = w >= 0 && fam == 1;
+            const unsigned b0 = __ballot_sync(0xffffffffu, isf);
+            if ((tid & 31) == 0) ball[tid >> 5] = b0;
+            U_s[tid] = -1; thr_s[tid] = -1;
+        }
         __syncthreads();
-        const int pos = (tid >= 32 ? __popc(ball[0]) : 0) + __popc(b0 & ((1u << (tid & 31)) - 1));
-        if (isf) fw[pos] = w;
-        if (tid == 0) nf_s = __popc(ball[0]) + __popc(ball[1]);
+        if (tid < 64) {
+            int w = -1, fam = -1;
+            if (tid < M && r >= 0 && r < P.Rcap) { w = P.W[(size_t)r * M + tid]; fam = P.famous[(size_t)r * M + tid]; }
+            const bool isf = w >= 0 && fam == 1;
+            const unsigned mine = ball[tid >> 5];
+            const int pos = (tid >= 32 ? __popc(ball[0]) : 0) + __popc(mine & ((1u << (tid & 31)) - 1));
+            if (isf) {
+                fw[pos] = w;
+                const int cw = P.creator[w];
+                st[pos] = P.stake[cw];
+                tbd_s[pos] = w > P.lastord[cw] ? 1 : 0;                  // w in tbd
+            }
+            if (tid == 0) nf_s = __popc(ball[0]) + __popc(ball[1]);
+        }
         __syncthreads();
         const int nf = nf_s;
-        {   // white = XOR of the famous witnesses' signatures, byte tid
+        for (int i = tid; i < nf * 64; i += 1024) {
+            const int fi = i >> 6, c = i & 63;
+            mat[fi][c] = c < M ? P.row[(size_t)fw[fi] * M + c] : -1;
+        }
+        if (tid < 64) {   // white = XOR of the famous witnesses' signatures, byte tid
             uint8_t x = 0;
             for (int i = 0; i < nf; i++) x ^= P.sig[(size_t)fw[i] * 64 + tid];
             P.seg_white[(size_t)si * 64 + tid] = x;
             P.seg_fw[(size_t)si * 64 + tid] = tid < nf ? fw[tid] : -1;
             if (tid == 0) { P.seg_nf[si] = nf; P.seg_start[si] = total; }
         }
-        int cnt = 0, cut = -1;
-        if (tid < M) {
-            const int c = tid;
-            int U = -1, thr = -1;
-            for (int i = 0; i < nf; i++) {
-                const int wi = fw[i];
-                const int v = P.row[(size_t)wi * M + c];
-                if (wi > P.lastord[P.creator[wi]]) U = max(U, v);        // w in tbd
-                if (v > thr) {       // is v seen by more than half the stake?  (:291-293)
+        __syncthreads();
+        {   // per chain c: reach U[c] and received-threshold thr[c], 16 thread groups x 64 chains
+            const int c = tid & 63, grp = tid >> 6;
+            int bestU = -1, bestT = -1;
+            for (int i = grp; i < nf; i += 16) {
+                const int v = mat[i][c];
+                if (tbd_s[i]) bestU = max(bestU, v);
+                if (v > bestT) {     // is v seen by more than half the stake?  (:291-293)
                     i64 acc = 0;
                     for (int k = 0; k < nf; k++)
-                        if (P.row[(size_t)fw[k] * M + c] >= v) acc += P.stake[P.creator[fw[k]]];
-                    if (2 * acc > P.tot) thr = v;
+                        if (mat[k][c] >= v) acc += st[k];
+                    if (2 * acc > P.tot) bestT = v;
                 }
             }
-            cut = min(U, thr);
-            const int lo = P.lastord[c];
+            if (bestU >= 0) atomicMax(&U_s[c], bestU);
+            if (bestT >= 0) atomicMax(&thr_s[c], bestT);
+        }
+        __syncthreads();
+        int cnt = 0, cut = -1;
+        if (tid < M) {
+            cut = min(U_s[tid], thr_s[tid]);
+            const int lo = P.lastord[tid];
             if (cut > lo) cnt = P.seq[cut] - (lo >= 0 ? P.seq[lo] : -1);
         }
-        cnts[tid] = cnt;
+        if (tid < 64) cnts[tid] = cnt;
         __syncthreads();
-        int off = total;
-        for (int i = 0; i < tid; i++) off += cnts[i];
         int tot_here = 0;
         for (int i = 0; i < 64; i++) tot_here += cnts[i];
-        if (cnt > 0) {
+        if (tid < 64 && cnt > 0) {
+            int off = total;
+            for (int i = 0; i < tid; i++) off += cnts[i];
             int x = cut;
             for (int j = 0; j < cnt; j++) {
                 P.batch_ev[off + j] = x;
