@@ -6,6 +6,7 @@
 #include "swirld_kernels.cuh"
 #include "swirld_divide.cuh"
 #include "swirld_levels.cuh"
+#include "swirld_cansee.cuh"
 
 #include <cstdlib>
 #include "../../include/swirld_b200.h"
@@ -39,6 +40,10 @@ struct sw_engine {
     GDesc *d_gdesc = nullptr;
     long long *d_dbg = nullptr;
     int divide_impl = 4;          // 4 = level-scheduled (default), 3 = per-event flags
+    int cansee_scan = 0;          // 1 = can_see by the blocked scan k_cs_* (SW_CANSEE_IMPL=scan), 0 = fused into the walker
+    int n_rowed = 0;              // events whose can_see row is complete (cansee_scan)
+    uint8_t *d_exported = nullptr;
+    int32_t *d_exp_list = nullptr, *d_exp_cnt = nullptr, *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_CM = nullptr, *d_cs_carry = nullptr;
     double *d_t = nullptr;
     uint8_t *d_sig = nullptr;
     int32_t *d_row = nullptr, *d_round = nullptr;
@@ -49,7 +54,7 @@ struct sw_engine {
     int32_t *d_W = nullptr, *d_rem = nullptr, *d_newc = nullptr;
     u64 *d_S = nullptr, *d_V = nullptr;
     int8_t *d_famous = nullptr;
-    uint8_t *d_consensus = nullptr, *d_done = nullptr;
+    uint8_t *d_consensus = nullptr, *d_done = nullptr, *d_coin = nullptr;
     i64 *d_stake = nullptr;
     int32_t *d_scal = nullptr;
     // find_order
@@ -115,6 +120,7 @@ void fold_spans(sw_engine *e) {
             if (s.cat == 0) e->stats.ms_divide_rounds += ms;
             else if (s.cat == 1) e->stats.ms_decide_fame += ms;
             else if (s.cat == 2) e->stats.ms_find_order += ms;
+            else if (s.cat == 3) { e->stats.ms_can_see += ms; e->stats.ms_divide_rounds += ms; }
         }
         e->pool.push_back(s.a); e->pool.push_back(s.b);
     }
@@ -141,12 +147,14 @@ int reset_state(sw_engine *e, bool keep_events = false) {
     CK(cudaMemsetAsync(e->d_famous_ev, 0xff, e->cap, e->stream));
     k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_idx, -1, (size_t)e->cap);
     k_fill_i32<<<1, 64, 0, e->stream>>>(e->d_lastord, -1, (size_t)e->M);
+    k_fill_i32<<<1, 64, 0, e->stream>>>(e->d_cs_carry, -1, (size_t)64);
     int32_t sc[SC_COUNT] = {0};
     sc[SC_MAX_ROUND] = -1;
     CK(cudaMemcpyAsync(e->d_scal, sc, sizeof sc, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->stats.kernel_launches += 3;
     e->n_divided = e->n_tx = 0;
+    e->n_rowed = 0;
     if (!keep_events) {
         e->n_events = 0;
         std::fill(e->h_head.begin(), e->h_head.end(), -1);
@@ -165,12 +173,40 @@ int launch_divide(sw_engine *e, const DivParams &P) {
     return 0;
 }
 
-template <int NC, bool UNIT>
+template <int NC, bool UNIT, bool ROWS>
 int launch_levels(sw_engine *e, const Div4Params &Q) {
-    const size_t smem = sizeof(LvSmem<NC>);
-    CK(cudaFuncSetAttribute(k_divide_levels<NC, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_divide_levels<NC, UNIT><<<1, LV_THREADS, smem, e->stream>>>(Q);
+    const size_t smem = sizeof(LvSmem<NC, ROWS>);
+    CK(cudaFuncSetAttribute(k_divide_levels<NC, UNIT, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_divide_levels<NC, UNIT, ROWS><<<1, LV_THREADS, smem, e->stream>>>(Q);
     CK(cudaGetLastError());
+    return 0;
+}
+
+// can_see rows of every appended event that does not have one yet: blocked scan (k_cs_*)
+template <int NC>
+int cansee_scan(sw_engine *e) {
+    const int first = e->n_rowed, n = e->n_events - e->n_rowed;
+    if (n <= 0) return 0;
+    CsParams C{};
+    C.M = e->M; C.first = first; C.n = n;
+    C.B = std::min(n, n >= 400000 ? 8192 : (n >= 100000 ? 4096 : 2048));
+    C.nb = (n + C.B - 1) / C.B;
+    C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.row = e->d_row;
+    C.exported = e->d_exported; C.exp_list = e->d_exp_list; C.exp_cnt = e->d_exp_cnt;
+    C.last = e->d_cs_last; C.Qtab = e->d_cs_Q; C.CM = e->d_cs_CM; C.carry = e->d_cs_carry;
+    CK(cudaMemsetAsync(e->d_exported + first, 0, (size_t)n, e->stream));
+    CK(cudaMemsetAsync(e->d_exp_cnt, 0, sizeof(int32_t) * (size_t)C.nb, e->stream));
+    cudaEvent_t a = get_event(e), b = get_event(e);
+    cudaEventRecord(a, e->stream);
+    k_cs_local<NC><<<C.nb, NC * 32, 0, e->stream>>>(C);
+    k_cs_collect<<<std::max(1, std::min(296, (n + 255) / 256)), 256, 0, e->stream>>>(C);
+    k_cs_boundary<NC><<<1, 1024, 0, e->stream>>>(C);
+    k_cs_fix<NC><<<dim3((C.B + CS_FIX_EVENTS - 1) / CS_FIX_EVENTS, C.nb), 256, 0, e->stream>>>(C);
+    cudaEventRecord(b, e->stream);
+    e->spans.push_back(TimedSpan{a, b, 3});
+    CK(cudaGetLastError());
+    e->stats.kernel_launches += 4;
+    e->n_rowed = e->n_events;
     return 0;
 }
 
@@ -193,8 +229,12 @@ int divide_levels(sw_engine *e, const DivParams &P) {
     Div4Params Q{};
     Q.d = P; Q.gdesc = e->d_gdesc; Q.lvl_start = e->d_lvl_start;
     e->stats.kernel_launches += 4;
-    if (e->NC == 1) return e->unit ? launch_levels<1, true>(e, Q) : launch_levels<1, false>(e, Q);
-    return e->unit ? launch_levels<2, true>(e, Q) : launch_levels<2, false>(e, Q);
+    if (e->cansee_scan) {
+        if (e->NC == 1) return e->unit ? launch_levels<1, true, false>(e, Q) : launch_levels<1, false, false>(e, Q);
+        return e->unit ? launch_levels<2, true, false>(e, Q) : launch_levels<2, false, false>(e, Q);
+    }
+    if (e->NC == 1) return e->unit ? launch_levels<1, true, true>(e, Q) : launch_levels<1, false, true>(e, Q);
+    return e->unit ? launch_levels<2, true, true>(e, Q) : launch_levels<2, false, true>(e, Q);
 }
 
 }  // namespace
@@ -230,6 +270,8 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
     if (per < 1) per = 1;
     e->Rcap = (int)std::min<i64>((i64)e->cap + 2, (i64)e->cap / per + 16);
     if (const char *impl = getenv("SW_DIVIDE_IMPL")) e->divide_impl = atoi(impl) == 3 ? 3 : 4;
+    if (const char *impl = getenv("SW_CANSEE_IMPL")) e->cansee_scan = strcmp(impl, "scan") == 0 ? 1 : 0;
+    if (e->divide_impl != 4) e->cansee_scan = 0;
     e->h_head.assign(M, -1);
     e->h_count.assign(M, 0);
     e->h_creator.reserve(e->cap);
@@ -242,11 +284,14 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64)); CK(dalloc(&e->d_height, cap));
         CK(dalloc(&e->d_hist, cap + 2)); CK(dalloc(&e->d_cursor, cap + 2)); CK(dalloc(&e->d_order, cap));
         CK(dalloc(&e->d_gpos, cap)); CK(dalloc(&e->d_lvl_start, cap + 2)); CK(dalloc(&e->d_gdesc, cap));
+        CK(dalloc(&e->d_exported, cap)); CK(dalloc(&e->d_exp_list, cap + 8192)); CK(dalloc(&e->d_exp_cnt, cap / 2048 + 4));
+        CK(dalloc(&e->d_cs_last, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_Q, (cap / 2048 + 5) * (size_t)M));
+        CK(dalloc(&e->d_cs_CM, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_carry, (size_t)64));
         CK(dalloc(&e->d_dbg, (size_t)16)); CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 16, e->stream));
         CK(dalloc(&e->d_row, cap * M)); CK(dalloc(&e->d_T, cap * M)); CK(dalloc(&e->d_SM, cap));
         CK(dalloc(&e->d_round, cap)); CK(dalloc(&e->d_wit, cap)); CK(dalloc(&e->d_famous_ev, cap));
         CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_S, RM)); CK(dalloc(&e->d_V, RM)); CK(dalloc(&e->d_famous, RM));
-        CK(dalloc(&e->d_consensus, (size_t)e->Rcap)); CK(dalloc(&e->d_done, (size_t)e->Rcap));
+        CK(dalloc(&e->d_consensus, (size_t)e->Rcap)); CK(dalloc(&e->d_done, (size_t)e->Rcap)); CK(dalloc(&e->d_coin, RM));
         CK(dalloc(&e->d_rem, (size_t)e->Rcap)); CK(dalloc(&e->d_newc, (size_t)e->Rcap));
         CK(dalloc(&e->d_stake, (size_t)M)); CK(dalloc(&e->d_scal, (size_t)SC_COUNT));
         CK(dalloc(&e->d_lastord, (size_t)64)); CK(dalloc(&e->d_tx, cap)); CK(dalloc(&e->d_idx, cap));
@@ -270,7 +315,7 @@ void sw_destroy(sw_engine *e) {
     fold_spans(e);
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
-    void *ptrs[] = {e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
+    void *ptrs[] = {e->d_cs_last, e->d_cs_Q, e->d_cs_CM, e->d_cs_carry, e->d_exported, e->d_exp_list, e->d_exp_cnt, e->d_coin, e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
                     e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_V, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
@@ -382,9 +427,15 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     P.p0 = e->d_p0; P.p1 = e->d_p1; P.creator = e->d_creator;
     P.row = e->d_row; P.T = e->d_T; P.SM = e->d_SM; P.round = e->d_round; P.wit = e->d_wit; P.W = e->d_W;
     P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.scal = e->d_scal; P.dbg = e->d_dbg;
+    if (const char *xf = getenv("SW_XFLAGS")) P.xflags = atoi(xf);
     StrongParams Q{};
     Q.M = e->M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
     Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
+    Q.coin = e->d_coin; Q.sig = e->d_sig;
+    if (e->cansee_scan && first + n > e->n_rowed) {
+        int rc = e->NC == 1 ? cansee_scan<1>(e) : cansee_scan<2>(e);
+        if (rc < 0) return rc;
+    }
     {
         Span sp(e, 0);
         int rc;
@@ -410,7 +461,7 @@ int sw_decide_fame(sw_engine *e, int32_t *new_c_out, int cap) {
     FameParams P{};
     P.M = e->M; P.Rcap = e->Rcap; P.C = e->C; P.W = e->d_W; P.S = e->d_S; P.famous = e->d_famous;
     P.famous_ev = e->d_famous_ev; P.consensus = e->d_consensus; P.done = e->d_done; P.rem = e->d_rem; P.V = e->d_V;
-    P.sig = e->d_sig; P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.newc = e->d_newc; P.scal = e->d_scal;
+    P.coin = e->d_coin; P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.newc = e->d_newc; P.scal = e->d_scal;
     {
         Span sp(e, 1);
         k_fame<<<1, 1024, 0, e->stream>>>(P);

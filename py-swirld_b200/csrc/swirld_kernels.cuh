@@ -40,6 +40,7 @@ struct DivParams {
     int unit;            // all stakes == 1
     int32_t *scal;       // SC_*
     long long *dbg;      // 16 cycle counters for profiling builds of the walker, may be NULL
+    int xflags;          // experiments only (env SW_XFLAGS): 1 = skip the T-table store, 2 = skip all HBM result stores
 };
 
 // ---------------------------------------------------------------- small helpers
@@ -64,6 +65,8 @@ struct StrongParams {
     const uint8_t *wit;
     const u64 *SM;
     u64 *S;              // [Rcap][M]
+    uint8_t *coin;       // [Rcap][M] coin bit of the witness: sig[0] >> 7 (swirld.py:272)
+    const uint8_t *sig;  // [cap][64]
     const i64 *stake;
     i64 tot2;
 };
@@ -75,7 +78,9 @@ __global__ void __launch_bounds__(256) k_strong(StrongParams P) {
     if (h >= P.first + P.n) return;
     if (!P.wit[h]) return;
     const int rh = P.round[h];
-    if (rh < 1 || rh >= P.Rcap) return;
+    if (rh < 0 || rh >= P.Rcap) return;
+    if (lane == 0) P.coin[(size_t)rh * P.M + P.creator[h]] = P.sig[(size_t)h * 64] >> 7;
+    if (rh < 1) return;
     const int M = P.M, r = rh - 1;
     u64 mk[NC];
     i64 st[NC], hits[NC];
@@ -124,7 +129,7 @@ struct FameParams {
     uint8_t *done;           // [Rcap] scratch
     int32_t *rem;            // [Rcap] scratch: undecided witnesses of the round
     u64 *V;                  // [Rcap][M] scratch
-    const uint8_t *sig;      // [cap][64]
+    const uint8_t *coin;     // [Rcap][M], written by k_strong
     const i64 *stake;
     i64 tot2;
     int unit;
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
         vw[buf][tid] = w;
         const u64 s = w >= 0 ? P.S[(size_t)r_ * M + tid] : 0ull;
         sv[buf][tid] = s;
-        vcoin[buf][tid] = w >= 0 ? (P.sig[(size_t)w * 64] >> 7) : 0;   // swirld.py:272
+        vcoin[buf][tid] = (tid < M && r_ <= max_r) ? P.coin[(size_t)r_ * M + tid] : 0;   // swirld.py:272
         vsum[buf][tid] = wsum(s, P.unit, stake_s);
     };
     if (tid < 2) s_lo2[tid] = max_c;

@@ -123,13 +123,23 @@ __global__ void k_lvl_desc(LvlParams P) {
 }
 
 // ---------------------------------------------------------------- the level walker
-template <int NC>
+// ROWS = the walker also computes the can_see rows (fused); otherwise they were produced by
+// the k_cs_* kernels (swirld_cansee.cuh) and the ring only carries T and the round.
+template <int NC, bool ROWS>
 struct __align__(16) LvSlot {
     int32_t row[NC * 32];
     u64 T[NC * 32];
     int32_t round;
     int32_t pad[3];
 };
+template <int NC>
+struct __align__(16) LvSlot<NC, false> {
+    u64 T[NC * 32];
+    int32_t round;
+    int32_t pad[3];
+};
+template <int NC, bool ROWS> struct LvOwnRows { int32_t r[3][LV_BATCH][NC * 32]; };   // row(h) of the batch's events
+template <int NC> struct LvOwnRows<NC, true> { int32_t r[1][1][4]; };
 
 struct __align__(16) LvDesc {  // per event of a batch, in shared memory
     int32_t h, cr, pa, pb;
@@ -137,9 +147,10 @@ struct __align__(16) LvDesc {  // per event of a batch, in shared memory
     int32_t pad0, pad1;
 };
 
-template <int NC>
+template <int NC, bool ROWS>
 struct LvSmem {
-    LvSlot<NC> slot[LV_RING + 2 * LV_STAGE];
+    LvSlot<NC, ROWS> slot[LV_RING + 2 * LV_STAGE];
+    __align__(16) LvOwnRows<NC, ROWS> own;
     LvDesc desc[3][LV_BATCH];
     int32_t lv_off[3][LV_MAXLEV + 1];
     int32_t nlev[3], bsize[3], bstart[3];
@@ -170,10 +181,10 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NC, bool UNIT>
+template <int NC, bool UNIT, bool ROWS>
 __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    LvSmem<NC> &S = *reinterpret_cast<LvSmem<NC> *>(smraw);
+    LvSmem<NC, ROWS> &S = *reinterpret_cast<LvSmem<NC, ROWS> *>(smraw);
     const DivParams &P = Q.d;
     constexpr int MS = NC * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -189,9 +200,11 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
     // ---- one-time init
     if (tid < MS) S.stake[tid] = tid < M ? P.stake[tid] : 0;
     for (int i = tid; i < (LV_RING + 2 * LV_STAGE) * MS; i += LV_THREADS) {   // padded columns stay (-1, 0)
-        S.slot[i / MS].row[i % MS] = -1;
+        if constexpr (ROWS) S.slot[i / MS].row[i % MS] = -1;
         S.slot[i / MS].T[i % MS] = 0;
     }
+    if constexpr (!ROWS)
+        for (int i = tid; i < 3 * LV_BATCH * MS; i += LV_THREADS) S.own.r[i / (LV_BATCH * MS)][(i / MS) % LV_BATCH][i % MS] = -1;
     int rmax = P.scal[SC_MAX_ROUND];
     int wbase = max(0, rmax - (SW_WC / 2 - 1));
     if (tid < 2) S.rmaxp[tid] = rmax;
@@ -256,17 +269,23 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
         const int ns = min(S.stage_cnt[sb], LV_STAGE);
         for (int s = warp - LV_COMP_WARPS; s < ns; s += LV_PREP_WARPS) {
             const int p = S.stage_p[sb][s];
-            LvSlot<NC> *dst = &S.slot[LV_RING + sb * LV_STAGE + s];
+            LvSlot<NC, ROWS> *dst = &S.slot[LV_RING + sb * LV_STAGE + s];
             for (int c = lane; c < M; c += 32) {
-                lv_cp_async4(&dst->row[c], P.row + (size_t)p * M + c);
+                if constexpr (ROWS) lv_cp_async4(&dst->row[c], P.row + (size_t)p * M + c);
                 lv_cp_async8(&dst->T[c], P.T + (size_t)p * M + c);
             }
             if (lane == 0) lv_cp_async4(&dst->round, P.round + p);
         }
+        if constexpr (!ROWS) {              // the batch's own can_see rows (made by k_cs_*)
+            for (int k = warp - LV_COMP_WARPS; k < bs; k += LV_PREP_WARPS) {
+                const int h = S.desc[db][k].h;
+                for (int c = lane; c < M; c += 32) lv_cp_async4(&S.own.r[db][k][c], P.row + (size_t)h * M + c);
+            }
+        }
     };
 
     // ---- one event, one warp (lane = member column, NC columns per lane)
-    auto process = [&](const LvDesc *dp, int slot_h, unsigned parity) {
+    auto process = [&](const LvDesc *dp, int slot_h, unsigned parity, const int32_t *own_row) {
         const int4 d0 = reinterpret_cast<const int4 *>(dp)[0];        // h, cr, pa, pb
         const int2 d1 = reinterpret_cast<const int2 *>(dp)[2];        // la, lb
         const int eh = d0.x, cr = d0.y, pa = d0.z, pb = d0.w, la = d1.x, lb = d1.y;
@@ -280,29 +299,37 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
             int va[NC], vb[NC];
             u64 ta[NC], tb[NC];
             int rb;
+#pragma unroll
+            for (int j = 0; j < NC; j++) { va[j] = -1; vb[j] = -1; }
             if (la >= 0) {
-                const LvSlot<NC> &A = S.slot[la];
+                const LvSlot<NC, ROWS> &A = S.slot[la];
                 ra = A.round;
 #pragma unroll
-                for (int j = 0; j < NC; j++) { va[j] = A.row[lane + 32 * j]; ta[j] = A.T[lane + 32 * j]; }
+                for (int j = 0; j < NC; j++) {
+                    if constexpr (ROWS) va[j] = A.row[lane + 32 * j];
+                    ta[j] = A.T[lane + 32 * j];
+                }
             } else {                                        // staging overflow: straight from HBM
                 ra = __ldcg(P.round + pa);
 #pragma unroll
                 for (int j = 0; j < NC; j++) {
-                    va[j] = act[j] ? __ldcg(P.row + (size_t)pa * M + lane + 32 * j) : -1;
+                    if constexpr (ROWS) va[j] = act[j] ? __ldcg(P.row + (size_t)pa * M + lane + 32 * j) : -1;
                     ta[j] = act[j] ? __ldcg(P.T + (size_t)pa * M + lane + 32 * j) : 0ull;
                 }
             }
             if (lb >= 0) {
-                const LvSlot<NC> &B = S.slot[lb];
+                const LvSlot<NC, ROWS> &B = S.slot[lb];
                 rb = B.round;
 #pragma unroll
-                for (int j = 0; j < NC; j++) { vb[j] = B.row[lane + 32 * j]; tb[j] = B.T[lane + 32 * j]; }
+                for (int j = 0; j < NC; j++) {
+                    if constexpr (ROWS) vb[j] = B.row[lane + 32 * j];
+                    tb[j] = B.T[lane + 32 * j];
+                }
             } else {
                 rb = __ldcg(P.round + pb);
 #pragma unroll
                 for (int j = 0; j < NC; j++) {
-                    vb[j] = act[j] ? __ldcg(P.row + (size_t)pb * M + lane + 32 * j) : -1;
+                    if constexpr (ROWS) vb[j] = act[j] ? __ldcg(P.row + (size_t)pb * M + lane + 32 * j) : -1;
                     tb[j] = act[j] ? __ldcg(P.T + (size_t)pb * M + lane + 32 * j) : 0ull;
                 }
             }
@@ -311,7 +338,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
             int cnt = 0;
 #pragma unroll
             for (int j = 0; j < NC; j++) {
-                rowh[j] = max(va[j], vb[j]);                                // swirld.py:203-205
+                if constexpr (ROWS) rowh[j] = max(va[j], vb[j]);            // swirld.py:203-205
                 t[j] = (ta[j] & ka) | (tb[j] & kb);
                 bool ss;                                                    // swirld.py:209-214
                 if (UNIT) ss = __popcll(t[j]) > (int)thr;
@@ -336,9 +363,13 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
             P.W[(size_t)rh * M + cr] = eh;
             atomicMax(&S.rmaxp[parity], rh);
         }
+        if constexpr (!ROWS) {                              // the finished row, from k_cs_*
+#pragma unroll
+            for (int j = 0; j < NC; j++) rowh[j] = own_row[lane + 32 * j];
+        }
         const u64 keep = promoted ? 0ull : ~0ull, own = 1ull << cr;
         u64 smask = 0;
-        LvSlot<NC> &H = S.slot[slot_h];
+        LvSlot<NC, ROWS> &H = S.slot[slot_h];
 #pragma unroll
         for (int j = 0; j < NC; j++) {
             const int c = lane + 32 * j;
@@ -348,7 +379,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
             const bool sm = wk >= 0 && rowh[j] >= wk;
             smask |= (u64)__ballot_sync(0xffffffffu, sm) << (32 * j);
             t[j] = (t[j] & keep) | (sm ? own : 0ull);
-            H.row[c] = rowh[j];                             // publish: what the next level reads
+            if constexpr (ROWS) H.row[c] = rowh[j];         // publish: what the next level reads
             H.T[c] = t[j];
         }
         if (lane == 0) H.round = rh;
@@ -357,10 +388,10 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
         for (int j = 0; j < NC; j++)
             if (act[j]) {
                 const size_t o = (size_t)eh * M + lane + 32 * j;
-                P.row[o] = rowh[j];
-                P.T[o] = t[j];
+                if constexpr (ROWS) { if (!(P.xflags & 2)) P.row[o] = rowh[j]; }
+                if (!(P.xflags & 3)) P.T[o] = t[j];
             }
-        if (lane == 0) {
+        if (lane == 0 && !(P.xflags & 2)) {
             P.round[eh] = rh;
             P.wit[eh] = wit ? 1 : 0;
             P.SM[eh] = smask;
@@ -382,7 +413,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
             for (int l = 0; l < nlev; ++l) {
                 const int hi = S.lv_off[db][l + 1];
                 for (int k = S.lv_off[db][l] + warp; k < hi; k += LV_COMP_WARPS) {
-                    process(&S.desc[db][k], (gb0 + k) % LV_RING, parity);
+                    process(&S.desc[db][k], (gb0 + k) % LV_RING, parity, ROWS ? nullptr : &S.own.r[ROWS ? 0 : db][ROWS ? 0 : k][0]);
                     c_nproc++;
                 }
                 __syncwarp();

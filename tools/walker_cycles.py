@@ -15,3 +15,4 @@ for rep in range(2):
     print('compute: proc %.1fM lbar %.1fM bbar %.1fM  nproc %d nlev %d nbatch %d'%(c[0]/1e6,c[1]/1e6,c[2]/1e6,c[3],c[4],c[5]))
     print('  per level: proc %.0f lbar %.0f ; per batch bbar %.0f ; proc per call %.0f'%(c[0]/c[4], c[1]/c[4], c[2]/c[5], c[0]/max(1,c[3])))
     print('prep per batch: prep %.0f wait %.0f bbar %.0f'%(c[9]/c[5],c[10]/c[5],c[11]/c[5]))
+    print('stats', {k: (round(v,2) if isinstance(v,float) else v) for k,v in st.items()})
