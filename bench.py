@@ -18,7 +18,8 @@ Trace: generator G1 (reference-sim gossip), seed 1 + rank.
             engine, appends each chunk from pinned host memory (H2D inside the timed
             region), runs divide_rounds + decide_fame per chunk and reads back
             round / witness / famous for all events (D2H inside the timed region).
-`roofline`: the dominant kernel k_divide (fused can_see + rounds), algorithmic bytes
+`roofline`: the dominant kernel k_divide_levels (level walker: can_see + rounds; its
+            counting-sort helpers and k_strong are bracketed with it), algorithmic bytes
             B(M) = 12M + 12 + 5 + M/8 per event over its mean
             launch duration, against MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline` / --impl reference: the reference is pure Python and cannot travel to
@@ -325,15 +326,19 @@ def bench_ours(args, wl, rank, world, local_rank):
                     "what": "reset + per chunk: sw_append (pinned host -> HBM) + sw_divide_rounds + sw_decide_fame; "
                             "then round/witness/famous of every event back to pinned host"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_divide (fused can_see + rounds), one launch per chunk",
+            "roofline": {"bound": "hbm", "kernel": "k_divide_levels (level walker: can_see rows + rounds + witnesses; "
+                                                   "one launch per chunk, bracketed with k_lvl_* and k_strong)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_event": bpe, "events_per_launch": K,
                          "ms_per_launch": ms_div / n_div_launch,
-                         "note": "latency-bound: one CTA walks the DAG in dependency order "
-                                 "(~53.6k dependent levels per 1M events at M=64)"},
+                         "note": "latency/issue-bound, not HBM-bound: one CTA walks ~53.7k dependent levels per 1M "
+                                 "events at M=64 (cycle accounting: profiles/, tools/walker_cycles.py)"},
             "kernel_ms_per_step": {"divide_rounds": ms_div / args.steps, "decide_fame": ms_fame / args.steps,
+                                   "can_see_scan": (st1["ms_can_see"] - st0["ms_can_see"]) / args.steps,
                                    "wall": wall_ms_max / args.steps},
+            "impl": {"divide": os.environ.get("SW_DIVIDE_IMPL", "4 (levels)"),
+                     "can_see": os.environ.get("SW_CANSEE_IMPL", "fused")},
             "cpu_baseline": {"value": n_cpu / s_cpu, "unit": "events/s", "cores": 1, "kind": "port",
                              "sample": "full trace (%d events), oracle/swirld_oracle.c single thread on a host with %d cpus"
                                        % (n_cpu, os.cpu_count())},

@@ -189,7 +189,7 @@ int cansee_scan(sw_engine *e) {
     if (n <= 0) return 0;
     CsParams C{};
     C.M = e->M; C.first = first; C.n = n;
-    C.B = std::min(n, n >= 400000 ? 8192 : (n >= 100000 ? 4096 : 2048));
+    C.B = std::min(n, n >= 200000 ? 4096 : 2048);
     C.nb = (n + C.B - 1) / C.B;
     C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.row = e->d_row;
     C.exported = e->d_exported; C.exp_list = e->d_exp_list; C.exp_cnt = e->d_exp_cnt;
@@ -427,7 +427,6 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     P.p0 = e->d_p0; P.p1 = e->d_p1; P.creator = e->d_creator;
     P.row = e->d_row; P.T = e->d_T; P.SM = e->d_SM; P.round = e->d_round; P.wit = e->d_wit; P.W = e->d_W;
     P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.scal = e->d_scal; P.dbg = e->d_dbg;
-    if (const char *xf = getenv("SW_XFLAGS")) P.xflags = atoi(xf);
     StrongParams Q{};
     Q.M = e->M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
     Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;

@@ -152,7 +152,7 @@ __device__ __forceinline__ void cs_complete_row(const CsParams &P, int x, int li
 template <int NC>
 __global__ void __launch_bounds__(1024, 1) k_cs_boundary(CsParams P) {
     constexpr int MS = NC * 32;
-    __shared__ int32_t Q[MS];
+    __shared__ int32_t Q[MS], CMs[MS];
     __shared__ int32_t S[MS][MS];
     __shared__ int cnt_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = P.M;
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(1024, 1) k_cs_boundary(CsParams P) {
         if (tid < MS) {                                      // tables for k_cs_fix
             int cm = -1;
             for (int m = 0; m < M; m++) cm = max(cm, S[m][tid]);
+            CMs[tid] = cm;
             if (tid < M) { P.CM[(size_t)blk * M + tid] = cm; P.Qtab[(size_t)blk * M + tid] = Q[tid]; }
         }
         if (tid == 0) cnt_s = P.exp_cnt[blk];
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(1024, 1) k_cs_boundary(CsParams P) {
         }
         __syncthreads();
         const int cnt = cnt_s;
-        for (int i = warp; i < cnt; i += 32) cs_complete_row<NC>(P, list[i], lim, lane, Q, S, nullptr);
+        for (int i = warp; i < cnt; i += 32) cs_complete_row<NC>(P, list[i], lim, lane, Q, S, CMs);
         __syncthreads();
         for (int i = tid; i < MS * MS; i += 1024) {          // heads for the next block
             const int m = i / MS, c = i % MS;

@@ -40,7 +40,6 @@ struct DivParams {
     int unit;            // all stakes == 1
     int32_t *scal;       // SC_*
     long long *dbg;      // 16 cycle counters for profiling builds of the walker, may be NULL
-    int xflags;          // experiments only (env SW_XFLAGS): 1 = skip the T-table store, 2 = skip all HBM result stores
 };
 
 // ---------------------------------------------------------------- small helpers

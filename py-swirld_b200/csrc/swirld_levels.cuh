@@ -153,7 +153,7 @@ struct LvSmem {
     __align__(16) LvOwnRows<NC, ROWS> own;
     LvDesc desc[3][LV_BATCH];
     int32_t lv_off[3][LV_MAXLEV + 1];
-    int32_t nlev[3], bsize[3], bstart[3];
+    int32_t nlev[3], bsize[3], bstart[3], nact[3];
     int32_t stage_cnt[2];
     int32_t stage_p[2][LV_STAGE];
     __align__(16) int32_t Wc[SW_WC][NC * 32];
@@ -238,6 +238,12 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
                 S.lv_off[db][lane + 1] = v - gb0;
                 if (lane == cnt - 1) S.bsize[db] = v - gb0;
             }
+            // widest level of the batch -> how many compute warps take part in its level barriers
+            const int prevv = __shfl_up_sync(0xffffffffu, v, 1);
+            int wdt = lane < cnt ? v - (lane == 0 ? gb0 : prevv) : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wdt = max(wdt, __shfl_xor_sync(0xffffffffu, wdt, o));
+            if (lane == 0) S.nact[db] = min(LV_COMP_WARPS, max(wdt, 1));
         }
         bar_named(2, LV_PREP_THREADS);
         const int cnt = S.nlev[db], gb0 = S.bstart[db], bs = S.bsize[db], ge = gb0 + bs;
@@ -276,8 +282,9 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
             }
             if (lane == 0) lv_cp_async4(&dst->round, P.round + p);
         }
-        if constexpr (!ROWS) {              // the batch's own can_see rows (made by k_cs_*)
-            for (int k = warp - LV_COMP_WARPS; k < bs; k += LV_PREP_WARPS) {
+        if constexpr (!ROWS) {              // can_see rows (made by k_cs_*) of the batch's FIRST level;
+            const int n0 = cnt > 0 ? S.lv_off[db][1] : 0;   // later levels prefetch theirs from the compute warps
+            for (int k = warp - LV_COMP_WARPS; k < n0; k += LV_PREP_WARPS) {
                 const int h = S.desc[db][k].h;
                 for (int c = lane; c < M; c += 32) lv_cp_async4(&S.own.r[db][k][c], P.row + (size_t)h * M + c);
             }
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
     };
 
     // ---- one event, one warp (lane = member column, NC columns per lane)
-    auto process = [&](const LvDesc *dp, int slot_h, unsigned parity, const int32_t *own_row) {
+    auto process = [&](const LvDesc *dp, int slot_h, unsigned parity, const int (&own_row)[NC]) {
         const int4 d0 = reinterpret_cast<const int4 *>(dp)[0];        // h, cr, pa, pb
         const int2 d1 = reinterpret_cast<const int2 *>(dp)[2];        // la, lb
         const int eh = d0.x, cr = d0.y, pa = d0.z, pb = d0.w, la = d1.x, lb = d1.y;
@@ -365,7 +372,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
         }
         if constexpr (!ROWS) {                              // the finished row, from k_cs_*
 #pragma unroll
-            for (int j = 0; j < NC; j++) rowh[j] = own_row[lane + 32 * j];
+            for (int j = 0; j < NC; j++) rowh[j] = own_row[j];
         }
         const u64 keep = promoted ? 0ull : ~0ull, own = 1ull << cr;
         u64 smask = 0;
@@ -384,14 +391,18 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
         }
         if (lane == 0) H.round = rh;
         // ---- stream the HBM copy straight from registers (fire and forget)
+        {
+            const size_t o = (size_t)eh * M + lane;
+            int32_t *grow = P.row + o;
+            u64 *gT = P.T + o;
 #pragma unroll
-        for (int j = 0; j < NC; j++)
-            if (act[j]) {
-                const size_t o = (size_t)eh * M + lane + 32 * j;
-                if constexpr (ROWS) { if (!(P.xflags & 2)) P.row[o] = rowh[j]; }
-                if (!(P.xflags & 3)) P.T[o] = t[j];
-            }
-        if (lane == 0 && !(P.xflags & 2)) {
+            for (int j = 0; j < NC; j++)
+                if (act[j]) {
+                    if constexpr (ROWS) grow[32 * j] = rowh[j];
+                    gT[32 * j] = t[j];
+                }
+        }
+        if (lane == 0) {
             P.round[eh] = rh;
             P.wit[eh] = wit ? 1 : 0;
             P.SM[eh] = smask;
@@ -408,20 +419,58 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
         if (nlev == 0) break;                               // uniform: written before the barrier
         const unsigned parity = (unsigned)b & 1u;
         long long t0 = clock64();
-        if (is_compute) {
+        const int nact = S.nact[db];
+        if (is_compute && warp < nact) {            // the other compute warps have nothing in this batch
             const int gb0 = S.bstart[db];
+            int nrow[NC];                                   // own row prefetched for the next level
+            bool have_n = false;
+#pragma unroll
+            for (int j = 0; j < NC; j++) nrow[j] = -1;
             for (int l = 0; l < nlev; ++l) {
-                const int hi = S.lv_off[db][l + 1];
-                for (int k = S.lv_off[db][l] + warp; k < hi; k += LV_COMP_WARPS) {
-                    process(&S.desc[db][k], (gb0 + k) % LV_RING, parity, ROWS ? nullptr : &S.own.r[ROWS ? 0 : db][ROWS ? 0 : k][0]);
+                const int lo = S.lv_off[db][l], hi = S.lv_off[db][l + 1];
+                int prow[NC];
+                bool have_p = false;
+#pragma unroll
+                for (int j = 0; j < NC; j++) prow[j] = -1;
+                if constexpr (!ROWS) {
+                    if (l + 1 < nlev && hi + warp < S.lv_off[db][l + 2]) {   // my event of the next level
+                        const int eh2 = S.desc[db][hi + warp].h;
+#pragma unroll
+                        for (int j = 0; j < NC; j++)
+                            if (act[j]) prow[j] = __ldcg(P.row + (size_t)eh2 * M + lane + 32 * j);
+                        have_p = true;
+                    }
+                }
+                for (int k = lo + warp; k < hi; k += nact) {
+                    int orow[NC];
+#pragma unroll
+                    for (int j = 0; j < NC; j++) orow[j] = -1;
+                    if constexpr (!ROWS) {
+                        if (l == 0) {
+#pragma unroll
+                            for (int j = 0; j < NC; j++) orow[j] = S.own.r[db][k][lane + 32 * j];
+                        } else if (k == lo + warp && have_n) {
+#pragma unroll
+                            for (int j = 0; j < NC; j++) orow[j] = nrow[j];
+                        } else {
+                            const int eh1 = S.desc[db][k].h;
+#pragma unroll
+                            for (int j = 0; j < NC; j++)
+                                if (act[j]) orow[j] = __ldcg(P.row + (size_t)eh1 * M + lane + 32 * j);
+                        }
+                    }
+                    process(&S.desc[db][k], (gb0 + k) % LV_RING, parity, orow);
                     c_nproc++;
                 }
+#pragma unroll
+                for (int j = 0; j < NC; j++) nrow[j] = prow[j];
+                have_n = have_p;
                 __syncwarp();
                 long long t1 = clock64(); c_proc += t1 - t0;
-                bar_named(1, LV_COMP_THREADS);
+                bar_named(1, nact * 32);
                 t0 = clock64(); c_lbar += t0 - t1; c_nlev++;
             }
-        } else {
+        } else if (!is_compute) {
             prep(b + 1);
             long long t2 = clock64(); c_prep += t2 - t0;
             lv_cp_async_wait_all();

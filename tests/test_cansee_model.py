@@ -61,7 +61,7 @@ def scan_launch(tr, first, n, B, row, carry, stats):
                 CM[blk] = np.maximum(CM[blk], row[Q[blk, m]])
         todo = {x for x in range(lim, min(lim + B, first + n)) if exported[x]} | {int(v) for v in last[blk] if v >= 0}
         for x in sorted(todo):
-            complete(x, lim, blk, False)
+            complete(x, lim, blk, True)
             exported[x] = True
         Q[blk + 1] = np.where(last[blk] >= 0, last[blk], Q[blk])
     for j in range(n):                                      # C: k_cs_fix
