@@ -54,6 +54,11 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_divide_levels launch at c3 (65536 events), from
+# the committed ncu --set full capture profiles/r01_k_divide_levels_ncu_full.md
+WALKER_DRAM_BYTES_PER_LAUNCH = 2365952 + 2083072
+
+
 def algorithmic_bytes_per_event(M):
     return 12 * M + 12 + 5 + M / 8.0
 
@@ -329,7 +334,10 @@ def bench_ours(args, wl, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "k_divide_levels (level walker: can_see rows + rounds + witnesses; "
                                                    "one launch per chunk, bracketed with k_lvl_* and k_strong)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": WALKER_DRAM_BYTES_PER_LAUNCH if (M == 64 and K == 65536) else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                           "k_divide_levels launch (profiles/r01_k_divide_levels_ncu_full.md)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_event": bpe, "events_per_launch": K,
                          "ms_per_launch": ms_div / n_div_launch,
                          "note": "latency/issue-bound, not HBM-bound: one CTA walks ~53.7k dependent levels per 1M "

@@ -173,13 +173,17 @@ int launch_divide(sw_engine *e, const DivParams &P) {
     return 0;
 }
 
-template <int NC, bool UNIT, bool ROWS>
-int launch_levels(sw_engine *e, const Div4Params &Q) {
+template <int NC, bool UNIT, bool ROWS, bool FULL>
+int launch_levels4(sw_engine *e, const Div4Params &Q) {
     const size_t smem = sizeof(LvSmem<NC, ROWS>);
-    CK(cudaFuncSetAttribute(k_divide_levels<NC, UNIT, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_divide_levels<NC, UNIT, ROWS><<<1, LV_THREADS, smem, e->stream>>>(Q);
+    CK(cudaFuncSetAttribute(k_divide_levels<NC, UNIT, ROWS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_divide_levels<NC, UNIT, ROWS, FULL><<<1, LV_THREADS, smem, e->stream>>>(Q);
     CK(cudaGetLastError());
     return 0;
+}
+template <int NC, bool UNIT, bool ROWS>
+int launch_levels(sw_engine *e, const Div4Params &Q) {
+    return e->M == NC * 32 ? launch_levels4<NC, UNIT, ROWS, true>(e, Q) : launch_levels4<NC, UNIT, ROWS, false>(e, Q);
 }
 
 // can_see rows of every appended event that does not have one yet: blocked scan (k_cs_*)

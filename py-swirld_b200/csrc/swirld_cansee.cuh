@@ -48,12 +48,11 @@ struct CsParams {
 template <int NC>
 __global__ void __launch_bounds__(NC * 32) k_cs_local(CsParams P) {
     constexpr int MS = NC * 32;
-    __shared__ int32_t tag[MS][MS];          // [member][column]: the event whose value is cached
-    __shared__ int32_t val[MS][MS];
+    __shared__ int2 tv[MS][MS];              // [member][column]: (event, its cached value); one LDS.64
     __shared__ int32_t sp0[CS_TILE], sp1[CS_TILE], scr[CS_TILE], scb[CS_TILE];
     const int c = threadIdx.x, M = P.M;
     const int s = P.first + blockIdx.x * P.B, e = min(s + P.B, P.first + P.n);
-    for (int m = 0; m < MS; m++) tag[m][c] = -1;          // private to this thread's column
+    for (int m = 0; m < MS; m++) tv[m][c] = make_int2(-1, -1);   // private to this thread's column
     for (int t0 = s; t0 < e; t0 += CS_TILE) {
         const int tn = min(CS_TILE, e - t0);
         __syncthreads();
@@ -70,19 +69,20 @@ __global__ void __launch_bounds__(NC * 32) k_cs_local(CsParams P) {
             const int h = t0 + i, pa = sp0[i], pb = sp1[i], cr = scr[i], cb = scb[i];
             int v = -1;
             if (pa >= 0) {
+                const int2 ca = tv[cr][c], cbv = tv[cb][c];   // both cached heads at once
                 int a, b;
-                if (pa >= s) a = tag[cr][c] == pa ? val[cr][c] : P.row[(size_t)pa * M + c];
+                if (pa >= s) a = ca.x == pa ? ca.y : P.row[(size_t)pa * M + c];
                 else a = c == cr ? pa : -1;                  // out-of-block parent: a leaf
-                if (pb >= s) b = tag[cb][c] == pb ? val[cb][c] : P.row[(size_t)pb * M + c];
+                if (pb >= s) b = cbv.x == pb ? cbv.y : P.row[(size_t)pb * M + c];
                 else b = c == cb ? pb : -1;
                 v = max(a, b);
             }
             if (c == cr) v = h;
-            tag[cr][c] = h; val[cr][c] = v;
+            tv[cr][c] = make_int2(h, v);
             P.row[(size_t)h * M + c] = v;
         }
     }
-    if (c < M) P.last[(size_t)blockIdx.x * M + c] = tag[c][c];   // member c's last event of the block
+    if (c < M) P.last[(size_t)blockIdx.x * M + c] = tv[c][c].x;  // member c's last event of the block
 }
 
 // per-block lists of the exported events

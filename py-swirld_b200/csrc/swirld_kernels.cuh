@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
     if (tid < 2) s_lo2[tid] = max_c;
     if (tid < 64) load_voters(max_c + 1, (max_c + 1) & 1);
     __syncthreads();
-    // 4 threads share one undecided witness (r, mx); each covers a quarter of the voters
+    // warps 0-1 fetch the next round's voters and advance the window; warps 2-31 vote:
+    // 4 threads share one undecided witness (r, mx), each covers a quarter of the voters
+    const int vt = tid - 64;                                    // voting thread id, < 0 for the fetch warps
     const int q = tid & 3, mq0 = q * 16;
     const unsigned qmask = 0xFu << (threadIdx.x & 28);
     for (int r_ = max_c + 1; r_ <= max_r; ++r_) {               // iter_voters, swirld.py:238-241
@@ -185,14 +187,14 @@ __global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
         // computed during the previous iteration (so it may lag: a harmless superset); the
         // next one is computed here while this round votes.
         const int lo = s_lo2[buf];
-        if (tid == 64) {
+        if (tid == 32) {
             int nlo = lo;
             while (nlo < r_ && P.rem[nlo] == 0) nlo++;
             s_lo2[buf ^ 1] = nlo;
         }
         const int nslots = (r_ - lo) * M;
-        for (int base = 0; base < nslots; base += 256) {        // iter_undetermined, :231-236
-            const int i = base + (tid >> 2);
+        for (int base = 0; base < nslots && vt >= 0; base += 240) {   // iter_undetermined, :231-236
+            const int i = base + (vt >> 2);
             bool live = i < nslots;
             int r = 0, mx = 0, x = -1;
             size_t slot = 0;

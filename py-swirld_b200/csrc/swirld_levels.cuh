@@ -181,7 +181,28 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NC, bool UNIT, bool ROWS>
+// ---- rare paths
+template <int NC, bool ROWS>
+__device__ __forceinline__ void lv_parent_from_hbm(const DivParams &P, int p, int lane, int &r, int (&v)[NC], u64 (&t)[NC]) {
+    r = __ldcg(P.round + p);
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const int c = lane + 32 * j;
+        if (ROWS) v[j] = c < P.M ? __ldcg(P.row + (size_t)p * P.M + c) : -1;
+        t[j] = c < P.M ? __ldcg(P.T + (size_t)p * P.M + c) : 0ull;
+    }
+}
+template <int NC>
+__device__ __forceinline__ void lv_witnesses_from_hbm(const DivParams &P, int rh, int lane, int (&w)[NC]) {
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const int c = lane + 32 * j;
+        w[j] = c < P.M ? __ldcg(P.W + (size_t)rh * P.M + c) : -1;
+    }
+}
+
+// FULL: M == 32*NC exactly (no padded member columns) -- drops the per-column predicates.
+template <int NC, bool UNIT, bool ROWS, bool FULL>
 __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
     extern __shared__ __align__(16) unsigned char smraw[];
     LvSmem<NC, ROWS> &S = *reinterpret_cast<LvSmem<NC, ROWS> *>(smraw);
@@ -195,7 +216,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
     const int nl = P.scal[SC_NSEG];         // written by k_lvl_scan
     bool act[NC];
 #pragma unroll
-    for (int j = 0; j < NC; j++) act[j] = lane + 32 * j < M;
+    for (int j = 0; j < NC; j++) act[j] = FULL || lane + 32 * j < M;
 
     // ---- one-time init
     if (tid < MS) S.stake[tid] = tid < M ? P.stake[tid] : 0;
@@ -316,14 +337,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
                     if constexpr (ROWS) va[j] = A.row[lane + 32 * j];
                     ta[j] = A.T[lane + 32 * j];
                 }
-            } else {                                        // staging overflow: straight from HBM
-                ra = __ldcg(P.round + pa);
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    if constexpr (ROWS) va[j] = act[j] ? __ldcg(P.row + (size_t)pa * M + lane + 32 * j) : -1;
-                    ta[j] = act[j] ? __ldcg(P.T + (size_t)pa * M + lane + 32 * j) : 0ull;
-                }
-            }
+            } else lv_parent_from_hbm<NC, ROWS>(P, pa, lane, ra, va, ta);   // staging overflow
             if (lb >= 0) {
                 const LvSlot<NC, ROWS> &B = S.slot[lb];
                 rb = B.round;
@@ -332,14 +346,7 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
                     if constexpr (ROWS) vb[j] = B.row[lane + 32 * j];
                     tb[j] = B.T[lane + 32 * j];
                 }
-            } else {
-                rb = __ldcg(P.round + pb);
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    if constexpr (ROWS) vb[j] = act[j] ? __ldcg(P.row + (size_t)pb * M + lane + 32 * j) : -1;
-                    tb[j] = act[j] ? __ldcg(P.T + (size_t)pb * M + lane + 32 * j) : 0ull;
-                }
-            }
+            } else lv_parent_from_hbm<NC, ROWS>(P, pb, lane, rb, vb, tb);
             r = max(ra, rb);                                                // swirld.py:200
             const u64 ka = ra == r ? ~0ull : 0ull, kb = rb == r ? ~0ull : 0ull;
             int cnt = 0;
@@ -360,11 +367,10 @@ __global__ void __launch_bounds__(LV_THREADS, 1) k_divide_levels(Div4Params Q) {
         const bool w_sm = rh >= wbase && rh < wbase + SW_WC;
         const int wslot = rh % SW_WC;
         int w[NC];
+        if (w_sm) {
 #pragma unroll
-        for (int j = 0; j < NC; j++) {
-            if (w_sm) w[j] = S.Wc[wslot][lane + 32 * j];
-            else w[j] = act[j] ? __ldcg(P.W + (size_t)rh * M + lane + 32 * j) : -1;
-        }
+            for (int j = 0; j < NC; j++) w[j] = S.Wc[wslot][lane + 32 * j];
+        } else lv_witnesses_from_hbm<NC>(P, rh, lane, w);            // a round outside the cached window
         if (wit && lane == 0) {                                              // swirld.py:222
             if (w_sm) S.Wc[wslot][cr] = eh;
             P.W[(size_t)rh * M + cr] = eh;

@@ -150,3 +150,36 @@ def _properties(tr, r):
     assert np.all(pos[tr.p0[ordered]] >= 0) and np.all(pos[tr.p1[ordered]] >= 0)
     # famous is only ever set on witnesses
     assert np.all(r["witness"][r["famous"] >= 0] == 1)
+
+
+def test_engine_edge_cases():
+    """Empty calls, exact-fit and exhausted capacity, ragged schedules, 64 members x tiny chunks."""
+    from swirld_b200 import engine, traces
+    tr = traces.gossip(64, 3000, 77)
+    e = engine.Engine(64, tr.N)                      # capacity == N exactly
+    with pytest.raises(engine.EngineError):          # decide_fame before any witness: max() of an empty dict
+        e.decide_fame()
+    e.divide_rounds(0, 0)                            # empty chunk: no-op
+    assert e.find_order([]) == 0
+    o = orc.Oracle(64)
+    o.append(tr)
+    sizes, first = [1, 2, 3, 5, 64, 1, 1, 700, 31, 33], 0
+    i = 0
+    while first < tr.N:
+        cnt = min(sizes[i % len(sizes)], tr.N - first)
+        i += 1
+        e.append_trace(tr, first, cnt)
+        e.divide_rounds(first, cnt)
+        o.divide_rounds(first, cnt)
+        nc_e, nc_o = e.decide_fame(), o.decide_fame()
+        assert sorted(nc_e) == sorted(nc_o)
+        e.find_order(nc_e)
+        o.find_order(nc_o)
+        first += cnt
+    assert_same(o.results(), e.results(), what="ragged schedule")
+    assert np.array_equal(o.can_see(), e.can_see())
+    with pytest.raises(engine.EngineError) as ei:    # one event too many
+        e.append([0], [1], [0], np.zeros(1), np.zeros((1, 64), np.uint8))
+    assert ei.value.code in (-5, -7, -6)
+    with pytest.raises(engine.EngineError):          # M above this build's limit
+        engine.Engine(65, 16)
