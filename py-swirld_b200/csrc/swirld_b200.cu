@@ -7,6 +7,7 @@
 #include "swirld_divide.cuh"
 #include "swirld_levels.cuh"
 #include "swirld_cansee.cuh"
+#include "swirld_rounds.cuh"
 
 #include <cstdlib>
 #include "../../include/swirld_b200.h"
@@ -39,7 +40,11 @@ struct sw_engine {
     int32_t *d_hist = nullptr, *d_cursor = nullptr, *d_order = nullptr, *d_gpos = nullptr, *d_lvl_start = nullptr;
     GDesc *d_gdesc = nullptr;
     long long *d_dbg = nullptr;
-    int divide_impl = 4;          // 4 = level-scheduled (default), 3 = per-event flags
+    int divide_impl = 4;          // 5 = round-batch on the whole GPU, 4 = level walker, 3 = per-event flags
+    int n_sm = 0;
+    int32_t *d_Wf = nullptr, *d_cev = nullptr, *d_rbmeta = nullptr, *d_rbtot = nullptr, *d_gchain = nullptr;   // round-batch state
+    ulonglong2 *d_sc = nullptr;
+    uint8_t *d_res = nullptr;
     int cansee_scan = 0;          // 1 = can_see by the blocked scan k_cs_* (SW_CANSEE_IMPL=scan), 0 = fused into the walker
     int n_rowed = 0;              // events whose can_see row is complete (cansee_scan)
     uint8_t *d_exported = nullptr;
@@ -148,6 +153,10 @@ int reset_state(sw_engine *e, bool keep_events = false) {
     k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_idx, -1, (size_t)e->cap);
     k_fill_i32<<<1, 64, 0, e->stream>>>(e->d_lastord, -1, (size_t)e->M);
     k_fill_i32<<<1, 64, 0, e->stream>>>(e->d_cs_carry, -1, (size_t)64);
+    k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_Wf, -1, RM);
+    CK(cudaMemsetAsync(e->d_rbtot, 0, sizeof(int32_t) * 64, e->stream));
+    k_fill_i32<<<64, 256, 0, e->stream>>>(e->d_gchain, -1, (size_t)64 * RB_RING);
+    CK(cudaMemsetAsync(e->d_sc, 0, sizeof(ulonglong2) * (size_t)e->cap, e->stream));
     int32_t sc[SC_COUNT] = {0};
     sc[SC_MAX_ROUND] = -1;
     CK(cudaMemcpyAsync(e->d_scal, sc, sizeof sc, cudaMemcpyHostToDevice, e->stream));
@@ -241,6 +250,36 @@ int divide_levels(sw_engine *e, const DivParams &P) {
     return e->unit ? launch_levels<2, true, true>(e, Q) : launch_levels<2, false, true>(e, Q);
 }
 
+// rounds of the chunk by the cooperative round-batch kernel (swirld_rounds.cuh)
+template <int NC, bool UNIT>
+int divide_round_batch(sw_engine *e, const DivParams &D) {
+    RbParams R{};
+    R.M = e->M; R.first = D.first; R.n = D.n; R.Rcap = e->Rcap;
+    const int grid = e->n_sm;
+    R.L = std::max(1, std::min(RB_LMAX, grid * (RB_THREADS / 32) / e->M));
+    R.row = e->d_row; R.p0 = e->d_p0; R.creator = e->d_creator; R.seq = e->d_seq; R.round = e->d_round;
+    R.Wf = e->d_Wf; R.sc = e->d_sc; R.cev = e->d_cev;
+    R.ccnt = e->d_rbmeta; R.cmin = e->d_rbmeta + 64; R.coff = e->d_rbmeta + 128;
+    R.ctot = e->d_rbtot; R.gchain = e->d_gchain;
+    R.res = e->d_res; R.stake = e->d_stake; R.tot2 = D.tot2; R.scal = e->d_scal;
+    R.wit = e->d_wit; R.W = e->d_W; R.SM = e->d_SM; R.dbg = e->d_dbg;
+    CK(cudaMemsetAsync(R.ccnt, 0, sizeof(int32_t) * 64, e->stream));
+    CK(cudaMemsetAsync(R.cmin, 0x7f, sizeof(int32_t) * 64, e->stream));
+    const int blocks = std::max(1, std::min(296, (D.n + 255) / 256));
+    k_rb_count<<<blocks, 256, 0, e->stream>>>(R);
+    k_rb_offsets<<<1, 32, 0, e->stream>>>(R);
+    k_rb_scatter<<<blocks, 256, 0, e->stream>>>(R);
+    CK(cudaGetLastError());
+    void *args[] = {(void *)&R};
+    CK(cudaLaunchCooperativeKernel((void *)k_rounds_batch<NC, UNIT>, dim3(grid), dim3(RB_THREADS), args, 0, e->stream));
+    k_rb_tail<<<blocks, 256, 0, e->stream>>>(R);
+    k_rb_witness<<<blocks, 256, 0, e->stream>>>(R);
+    k_rb_seenmask<NC><<<(D.n + 7) / 8, 256, 0, e->stream>>>(R);
+    CK(cudaGetLastError());
+    e->stats.kernel_launches += 7;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -273,9 +312,10 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
     i64 per = std::min<i64>(M, (2 * e->tot) / 3 + 1);
     if (per < 1) per = 1;
     e->Rcap = (int)std::min<i64>((i64)e->cap + 2, (i64)e->cap / per + 16);
-    if (const char *impl = getenv("SW_DIVIDE_IMPL")) e->divide_impl = atoi(impl) == 3 ? 3 : 4;
+    if (const char *impl = getenv("SW_DIVIDE_IMPL")) { int v = atoi(impl); e->divide_impl = (v == 3 || v == 5) ? v : 4; }
     if (const char *impl = getenv("SW_CANSEE_IMPL")) e->cansee_scan = strcmp(impl, "scan") == 0 ? 1 : 0;
-    if (e->divide_impl != 4) e->cansee_scan = 0;
+    if (e->divide_impl == 3) e->cansee_scan = 0;
+    if (e->divide_impl == 5) e->cansee_scan = 1;     // the round-batch kernel reads finished can_see rows
     e->h_head.assign(M, -1);
     e->h_count.assign(M, 0);
     e->h_creator.reserve(e->cap);
@@ -291,6 +331,10 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(dalloc(&e->d_exported, cap)); CK(dalloc(&e->d_exp_list, cap + 8192)); CK(dalloc(&e->d_exp_cnt, cap / 2048 + 4));
         CK(dalloc(&e->d_cs_last, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_Q, (cap / 2048 + 5) * (size_t)M));
         CK(dalloc(&e->d_cs_CM, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_carry, (size_t)64));
+        CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, cap)); CK(dalloc(&e->d_rbmeta, (size_t)256));
+        CK(dalloc(&e->d_sc, cap)); CK(dalloc(&e->d_res, (size_t)2 * 64 * RB_LMAX));
+        CK(dalloc(&e->d_rbtot, (size_t)64)); CK(dalloc(&e->d_gchain, (size_t)64 * RB_RING));
+        CK(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
         CK(dalloc(&e->d_dbg, (size_t)16)); CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 16, e->stream));
         CK(dalloc(&e->d_row, cap * M)); CK(dalloc(&e->d_T, cap * M)); CK(dalloc(&e->d_SM, cap));
         CK(dalloc(&e->d_round, cap)); CK(dalloc(&e->d_wit, cap)); CK(dalloc(&e->d_famous_ev, cap));
@@ -319,7 +363,7 @@ void sw_destroy(sw_engine *e) {
     fold_spans(e);
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
-    void *ptrs[] = {e->d_cs_last, e->d_cs_Q, e->d_cs_CM, e->d_cs_carry, e->d_exported, e->d_exp_list, e->d_exp_cnt, e->d_coin, e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
+    void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_CM, e->d_cs_carry, e->d_exported, e->d_exp_list, e->d_exp_cnt, e->d_coin, e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
                     e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_V, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
@@ -442,7 +486,10 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     {
         Span sp(e, 0);
         int rc;
-        if (e->divide_impl == 4) rc = divide_levels(e, P);
+        if (e->divide_impl == 5)
+            rc = e->NC == 1 ? (e->unit ? divide_round_batch<1, true>(e, P) : divide_round_batch<1, false>(e, P))
+                            : (e->unit ? divide_round_batch<2, true>(e, P) : divide_round_batch<2, false>(e, P));
+        else if (e->divide_impl == 4) rc = divide_levels(e, P);
         else rc = e->NC == 1 ? (e->unit ? launch_divide<1, true>(e, P) : launch_divide<1, false>(e, P))
                              : (e->unit ? launch_divide<2, true>(e, P) : launch_divide<2, false>(e, P));
         if (rc < 0) return rc;
