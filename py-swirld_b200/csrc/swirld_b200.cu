@@ -257,9 +257,12 @@ int divide_round_batch(sw_engine *e, const DivParams &D) {
     R.M = e->M; R.first = D.first; R.n = D.n; R.Rcap = e->Rcap;
     const int grid = e->n_sm;
     R.L = std::max(1, std::min(RB_LMAX, grid * (RB_THREADS / 32) / e->M));
+    R.maxmiss = RB_MAXMISS;
+    if (const char *v = getenv("SW_RB_L")) R.L = std::max(1, std::min(R.L, atoi(v)));          // tuning knobs
+    if (const char *v = getenv("SW_RB_MAXMISS")) R.maxmiss = std::max(0, atoi(v));
     R.row = e->d_row; R.p0 = e->d_p0; R.creator = e->d_creator; R.seq = e->d_seq; R.round = e->d_round;
     R.Wf = e->d_Wf; R.sc = e->d_sc; R.cev = e->d_cev;
-    R.ccnt = e->d_rbmeta; R.cmin = e->d_rbmeta + 64; R.coff = e->d_rbmeta + 128;
+    R.ccnt = e->d_rbmeta; R.cmin = e->d_rbmeta + 64; R.coff = e->d_rbmeta + 128; R.bar = reinterpret_cast<unsigned *>(e->d_rbmeta + 224);
     R.ctot = e->d_rbtot; R.gchain = e->d_gchain;
     R.res = e->d_res; R.stake = e->d_stake; R.tot2 = D.tot2; R.scal = e->d_scal;
     R.wit = e->d_wit; R.W = e->d_W; R.SM = e->d_SM; R.dbg = e->d_dbg;
@@ -335,7 +338,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(dalloc(&e->d_sc, cap)); CK(dalloc(&e->d_res, (size_t)2 * 64 * RB_LMAX));
         CK(dalloc(&e->d_rbtot, (size_t)64)); CK(dalloc(&e->d_gchain, (size_t)64 * RB_RING));
         CK(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
-        CK(dalloc(&e->d_dbg, (size_t)16)); CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 16, e->stream));
+        CK(dalloc(&e->d_dbg, (size_t)40)); CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 40, e->stream));
         CK(dalloc(&e->d_row, cap * M)); CK(dalloc(&e->d_T, cap * M)); CK(dalloc(&e->d_SM, cap));
         CK(dalloc(&e->d_round, cap)); CK(dalloc(&e->d_wit, cap)); CK(dalloc(&e->d_famous_ev, cap));
         CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_S, RM)); CK(dalloc(&e->d_V, RM)); CK(dalloc(&e->d_famous, RM));
@@ -662,7 +665,7 @@ int sw_debug_counters(sw_engine *e, int64_t *out16, int clear) {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMemcpy(out16, e->d_dbg, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
-    if (clear) CK(cudaMemset(e->d_dbg, 0, sizeof(long long) * 16));
+    if (clear) CK(cudaMemset(e->d_dbg, 0, sizeof(long long) * 40));
     return SW_OK;
 }
 

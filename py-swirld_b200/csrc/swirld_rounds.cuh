@@ -38,10 +38,10 @@ namespace cg = cooperative_groups;
 #define RB_LMAX 64          // pending events tested per chain and step (at most)
 #define RB_THREADS 512       // 16 warps per CTA, one CTA per SM
 #define RB_RING 256          // per-member ring of recent events (what precedes the chunk)
-#define RB_MAXMISS 8         // an event with more unprepared S_r masks than this waits for a later step
+#define RB_MAXMISS 0         // an event with more unprepared S_r masks than this waits for a later step
 
 struct RbParams {
-    int M, first, n, Rcap, L;
+    int M, first, n, Rcap, L, maxmiss;
     const int32_t *row, *p0, *creator, *seq;
     int32_t *round;             // [cap] out
     int32_t *Wf;                // [Rcap][M] first event of round >= r per member
@@ -51,7 +51,8 @@ struct RbParams {
     int32_t *ctot;              // [64] events of the member so far (1 + its largest seq)
     int32_t *gchain;            // [64][RB_RING] the member's most recent events by seq % RB_RING
     int32_t *coff;              // [65]
-    uint8_t *res;               // [2][64 * RB_LMAX]
+    unsigned *bar;              // grid barrier counter of k_rounds_batch (zeroed by k_rb_offsets)
+    uint8_t *res;               // per-step results of k_rounds_batch, 2 x (64 x u64 + 64 x int)
     const i64 *stake;
     i64 tot2;
     int32_t *scal;
@@ -84,6 +85,7 @@ __global__ void k_rb_offsets(RbParams P) {       // one warp
     P.coff[lane] = sa - a;
     P.coff[lane + 32] = tot_a + sb - b;
     if (lane == 31) P.coff[64] = tot_a + sb;
+    if (lane == 0) *P.bar = 0;
 }
 __global__ void k_rb_scatter(RbParams P) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.n; j += gridDim.x * blockDim.x) {
@@ -100,28 +102,60 @@ __global__ void k_rb_tail(RbParams P) {
     }
 }
 
+// 32x32 bit-matrix transpose across a warp: lane i gives row i, gets column i (bit b = row b's bit i)
+__device__ __forceinline__ unsigned rb_transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const unsigned m0 = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~m0) | ((y & ~m0) >> s)) : ((x & m0) | ((y & m0) << s));
+    }
+    return x;
+}
+
+// Grid-wide barrier for the co-resident (cooperatively launched) grid.  *ctr is zero at launch and
+// counts arrivals for ever; the caller keeps the running target.  The whole of warp 0 polls, so no
+// warp leaves the barrier split in two (cooperative_groups' grid.sync() lets thread 0 spin alone and
+// its warp then runs every later shuffle on the slow divergent path).
+__device__ __forceinline__ void rb_grid_barrier(unsigned *ctr, unsigned &target) {
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(ctr, 1u); }
+        __syncwarp();
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while ((int)(v - target) < 0);
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ u64 rb_key(int r) { return (u64)(r + 1) * 0x9E3779B97F4A7C15ull; }
 
 template <int NC, bool UNIT>
 __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
-    cg::grid_group grid = cg::this_grid();
     __shared__ int cur[64], pos[64], len[64], off[64];
-    __shared__ int Wl[RB_WR][64];
+    __shared__ int Wl[RB_WR][64], Wls[RB_WR][64];             // Wf of the last RB_WR rounds and the chain seq of its entries
     __shared__ i64 stake_s[64];
-    __shared__ int s_rmin, s_newtop, s_nfin[64], s_base[64];
-    __shared__ int cmin_s[64], ctot_s[64], ra_lo[64], ra_pre[65];
+    __shared__ int s_nfin[64], s_base[64];
+    __shared__ int cmin_s[64], ctot_s[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M, L = P.L;
     const int gw = blockIdx.x * (blockDim.x >> 5) + warp, nw = gridDim.x * (blockDim.x >> 5);
     const i64 thr = P.tot2 / 3;
     const bool lead = blockIdx.x == 0;
+    // per-step results, double buffered: first hit of a chain as (position << 32 | event), first deferred position
+    u64 *hitmin = reinterpret_cast<u64 *>(P.res);             // [2][64]
+    int *unkmin = reinterpret_cast<int *>(P.res + 2 * 64 * sizeof(u64));   // [2][64]
 
     int rtop = max(P.scal[SC_MAX_ROUND], 0);
     for (int i = tid; i < RB_WR * 64; i += blockDim.x) {
         const int slot = i >> 6, c = i & 63;
         // the round of (rtop-RB_WR, rtop] that maps to this slot
         const int r = rtop - ((rtop - slot) & (RB_WR - 1));
-        Wl[slot][c] = (c < M && r >= 0 && r < P.Rcap) ? __ldcg(P.Wf + (size_t)r * M + c) : -1;
+        const int w = (c < M && r >= 0 && r < P.Rcap) ? __ldcg(P.Wf + (size_t)r * M + c) : -1;
+        Wl[slot][c] = w;
+        Wls[slot][c] = w >= 0 ? P.seq[w] : 0;
     }
     if (tid < 64) {
         const int c = tid;
@@ -137,27 +171,28 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         off[c] = o; len[c] = l; pos[c] = 0; cur[c] = cu;
         cmin_s[c] = c < M ? P.cmin[c] : 0; ctot_s[c] = c < M ? P.ctot[c] : 0;
     }
+    if (lead && tid < 128) { hitmin[tid] = ~0ull; unkmin[tid] = 0x7fffffff; }
     __syncthreads();
     if (tid < M && len[tid] > 0 && cur[tid] == 0) {          // a member's root opens round 0 for it
         const int h0 = P.cev[off[tid]];
         if (P.p0[h0] < 0) {
-            if (rtop < RB_WR) Wl[0][tid] = h0;
+            if (rtop < RB_WR) { Wl[0][tid] = h0; Wls[0][tid] = P.seq[h0]; }
             if (lead) P.Wf[tid] = h0;
         }
     }
-    grid.sync();                                              // (late roots write the global table only)
-    if (rtop >= RB_WR && tid < M) { /* round 0 is outside the mirror: nothing to refresh */ }
+    unsigned bar_target = 0;
+    rb_grid_barrier(P.bar, bar_target);                       // (late roots write the global table only)
 
+    auto in_mirror = [&](int r) -> bool { return r > rtop - RB_WR && r <= rtop; };
     auto wrow = [&](int r, int c) -> int {                    // Wf_r[c]
-        if (r > rtop - RB_WR && r <= rtop) return Wl[r & (RB_WR - 1)][c];
+        if (in_mirror(r)) return Wl[r & (RB_WR - 1)][c];
         return __ldcg(P.Wf + (size_t)r * M + c);
     };
 
-    long long c_miss = 0, c_lastmiss = 0;
-    // ---- P_r(h) by one warp
-    auto eval = [&](int h, int r, bool may_defer) -> int {
-        const int cr = P.creator[h], pa = P.p0[h];
-        int W[NC], pre[NC];
+    long long c_miss = 0, tG0 = 0, tG1 = 0, c_g = 0, c_gmax = 0;
+    // ---- P_r(h) by one warp; pre = can_see row of h with the own column set back to the self-parent
+    auto eval = [&](const int (&pre)[NC], int r, bool may_defer) -> int {
+        int W[NC];
         bool live[NC];
         u64 m[NC];
         i64 lv = 0;
@@ -165,8 +200,6 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         for (int j = 0; j < NC; j++) {
             const int c = lane + 32 * j;
             W[j] = c < M ? wrow(r, c) : -1;
-            pre[j] = c < M ? __ldcg(P.row + (size_t)h * M + c) : -1;
-            if (c == cr) pre[j] = pa;
             live[j] = W[j] >= 0 && pre[j] >= W[j];
             m[j] = 0;
             if (UNIT) lv += __popc(__ballot_sync(0xffffffffu, live[j]));
@@ -177,6 +210,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
                 lv += s;
             }
         }
+        tG0 = clock64(); tG1 = tG0;
         if (lv <= thr) return 0;                              // hits[c_] <= stake of the live members
         const u64 key = rb_key(r);
         bool valid[NC];
@@ -189,12 +223,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
                 m[j] = e.x;
             }
         }
+        __syncwarp();
         {   // an event far ahead of the tested windows sees events nobody prepared: leave it for a later step
             int nm = 0;
 #pragma unroll
             for (int j = 0; j < NC; j++) nm += __popc(__ballot_sync(0xffffffffu, live[j] && !valid[j]));
-            c_lastmiss = nm;
-            if (may_defer && nm > RB_MAXMISS) return 2;       // (never the chain's first pending event: progress)
+            tG1 = clock64();
+            if (may_defer && nm > P.maxmiss) return 2;       // (never the chain's first pending event: progress)
         }
 #pragma unroll
         for (int jj = 0; jj < NC; jj++) {                     // cache misses: compute S_r(k) together,
@@ -225,18 +260,28 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
                 }
             }
         }
+        __syncwarp();                                         // (reconverge: the shuffles below must not take the divergent path)
+        // hits[c_] = stake of the live members whose mask has bit c_: transpose the (member x column)
+        // bit matrix in 32x32 blocks across the lanes, then lane c_ owns its column as NC words
+        unsigned T[NC][NC];                                   // T[jj][j]: bit b = member jj*32+b sees column j*32+lane
+#pragma unroll
+        for (int jj = 0; jj < NC; jj++) {
+            const u64 mine = live[jj] ? m[jj] : 0ull;         // a member that is not live contributes nothing
+#pragma unroll
+            for (int j = 0; j < NC; j++) T[jj][j] = rb_transpose32((unsigned)(mine >> (32 * j)), lane);
+        }
         i64 hits[NC];
 #pragma unroll
-        for (int j = 0; j < NC; j++) hits[j] = 0;
+        for (int j = 0; j < NC; j++) {
+            hits[j] = 0;
+            if (UNIT) {
 #pragma unroll
-        for (int jj = 0; jj < NC; jj++) {                     // column sums over the live members' masks
-            const u64 mine = live[jj] ? m[jj] : 0ull;         // a member that is not live contributes nothing
+                for (int jj = 0; jj < NC; jj++) hits[j] += __popc(T[jj][j]);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < NC; jj++)
 #pragma unroll 8
-            for (int l = 0; l < 32; l++) {
-                const u64 mm = __shfl_sync(0xffffffffu, mine, l);
-                const i64 st = UNIT ? 1 : stake_s[jj * 32 + l];
-#pragma unroll
-                for (int j = 0; j < NC; j++) hits[j] += ((mm >> (lane + 32 * j)) & 1) ? st : 0;
+                    for (int b = 0; b < 32; b++) hits[j] += ((T[jj][j] >> b) & 1) ? stake_s[jj * 32 + b] : 0;
             }
         }
         int cnt = 0;
@@ -245,46 +290,75 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         return (i64)cnt > thr ? 1 : 0;
     };
 
-    long long c_eval = 0, c_sync = 0, c_upd = 0, c_nev = 0, c_steps = 0, c_maxev = 0, c_sumev = 0;
+    long long c_t[6] = {0, 0, 0, 0, 0, 0}, c_nev = 0, c_steps = 0, c_maxev = 0, c_sumev = 0, c_def = 0;
     for (int step = 0;; ++step) {
         const long long t0 = clock64();
-        // ---- lowest open round
-        if (warp == 0) {
-            int a = 0x7fffffff;
-            for (int c = lane; c < M; c += 32) if (pos[c] < len[c]) a = min(a, cur[c]);
+        // ---- lowest open round (every warp for itself: the chain state is identical in all CTAs)
+        int rmin = 0x7fffffff;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
-            if (lane == 0) s_rmin = a;
+        for (int j = 0; j < 2; j++) {
+            const int c = lane + 32 * j;
+            if (c < M && pos[c] < len[c]) rmin = min(rmin, cur[c]);
         }
-        __syncthreads();
-        const int rmin = s_rmin;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
         if (rmin == 0x7fffffff) break;                        // every chain is done
-        uint8_t *res = P.res + (size_t)(step & 1) * 64 * RB_LMAX;
-        // ---- S_rmin(k) of every event the tests below can meet: per member, its events from
-        //      Wf_rmin[c] up to the end of its pending window (one warp per event, all SMs)
-        if (tid < 64) {
+        const int buf = step & 1;
+        // ---- this warp's test of the step: fetch its inputs now, they are needed after the barrier
+        const int tc = gw / L, tj = gw - tc * L;              // M * L <= nw: one (chain, position) per warp
+        bool act = false;
+        int th = -1, tpa = -1, tpre[NC];
+        if (tc < M && pos[tc] < len[tc] && cur[tc] == rmin && pos[tc] + tj < len[tc]) {
+            act = true;
+            th = P.cev[off[tc] + pos[tc] + tj];
+            tpa = P.p0[th];
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const int c = lane + 32 * j;
+                tpre[j] = c < M ? __ldcg(P.row + (size_t)th * M + c) : -1;
+            }
+        }
+        // ---- S_rmin(k) of every event the tests can meet: per member, its events from Wf_rmin[c] up to
+        //      the end of its pending window (one warp per event, all SMs).  Ranges in registers:
+        //      lane holds members lane and lane+32.
+        int rlo[2], rcnt[2], rinc[2];
+        const bool mir = in_mirror(rmin);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int c = lane + 32 * j;
             int lo = 0, cnt = 0;
-            if (tid < M) {
-                const int w = wrow(rmin, tid);
+            if (c < M) {
+                const int w = wrow(rmin, c);
                 if (w >= 0) {
-                    lo = __ldcg(P.seq + w);
-                    const int hi = len[tid] > 0 ? cmin_s[tid] + min(len[tid], pos[tid] + L) : ctot_s[tid];
+                    lo = mir ? Wls[rmin & (RB_WR - 1)][c] : __ldcg(P.seq + w);
+                    const int hi = len[c] > 0 ? cmin_s[c] + min(len[c], pos[c] + L) : ctot_s[c];
                     cnt = max(0, min(hi - lo, RB_RING));
                 }
             }
-            ra_lo[tid] = lo; ra_pre[tid + 1] = cnt;
+            rlo[j] = lo; rcnt[j] = cnt;
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+            rinc[j] = inc;
         }
-        __syncthreads();
-        if (tid == 0) { ra_pre[0] = 0; for (int c = 0; c < 64; c++) ra_pre[c + 1] += ra_pre[c]; }
-        __syncthreads();
+        const int totA = __shfl_sync(0xffffffffu, rinc[0], 31);
+        rinc[1] += totA;
+        const int total = __shfl_sync(0xffffffffu, rinc[1], 31);
+        const long long tA0 = clock64();
         {
-            const int total = ra_pre[64];
             const u64 key = rb_key(rmin);
             for (int i = gw; i < total; i += nw) {
-                int c = 0;                                     // member whose range holds candidate i
-#pragma unroll
-                for (int b = 32; b > 0; b >>= 1) if (c + b < 64 && ra_pre[c + b] <= i) c += b;
-                const int sq = ra_lo[c] + (i - ra_pre[c]);
+                // member whose range holds candidate i: the first with inclusive prefix > i
+                int c, base, lo;
+                if (i < totA) {
+                    c = __popc(__ballot_sync(0xffffffffu, rinc[0] <= i));
+                    base = __shfl_sync(0xffffffffu, rinc[0] - rcnt[0], c); lo = __shfl_sync(0xffffffffu, rlo[0], c);
+                } else {
+                    const int l = __popc(__ballot_sync(0xffffffffu, rinc[1] <= i));
+                    c = 32 + l;
+                    base = __shfl_sync(0xffffffffu, rinc[1] - rcnt[1], l); lo = __shfl_sync(0xffffffffu, rlo[1], l);
+                }
+                const int sq = lo + (i - base);
                 int k;
                 if (len[c] > 0 && sq >= cmin_s[c]) k = P.cev[off[c] + sq - cmin_s[c]];
                 else {      // before the chunk: the ring holds the member's last RB_RING events of the earlier chunks
@@ -303,98 +377,88 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
                 if (lane == 0) P.sc[k] = make_ulonglong2(mask, mask ^ key);
             }
         }
-        grid.sync();
+        const long long tA1 = clock64();
+        rb_grid_barrier(P.bar, bar_target);
+        const long long tS1 = clock64();
         // ---- test the pending windows
-        for (int e = gw; e < M * L; e += nw) {
-            const int c = e / L, j = e % L;
-            if (pos[c] < len[c] && cur[c] == rmin && pos[c] + j < len[c]) {
-                const int h = P.cev[off[c] + pos[c] + j];
-                const long long e0 = clock64();
-                const int hit = P.p0[h] >= 0 ? eval(h, rmin, j > 0) : 0;
-                const long long e1 = clock64() - e0;
-                c_maxev = e1 > c_maxev ? e1 : c_maxev; c_sumev += e1;
-                if (P.dbg && lane == 0 && e1 > 20000) {        // census of the slow tests
-                    atomicAdd((unsigned long long *)P.dbg + 9, 1ull);
-                    atomicAdd((unsigned long long *)P.dbg + 10, (unsigned long long)j);
-                    atomicAdd((unsigned long long *)P.dbg + 11, (unsigned long long)(hit == 2));
-                    atomicAdd((unsigned long long *)P.dbg + 12, (unsigned long long)c_lastmiss);
-                }
-                if (lane == 0) res[c * RB_LMAX + j] = (uint8_t)hit;
-                c_nev++;
+        if (act) {
+            int hit = 0;
+            if (tpa >= 0) {
+#pragma unroll
+                for (int j = 0; j < NC; j++) if (lane + 32 * j == tc) tpre[j] = tpa;
+                hit = eval(tpre, rmin, tj > 0);
             }
+            if (lane == 0) {
+                if (hit == 1) atomicMin(hitmin + buf * 64 + tc, ((u64)tj << 32) | (unsigned)th);
+                if (hit == 2) atomicMin(unkmin + buf * 64 + tc, tj);
+            }
+            const long long e1 = clock64() - tS1;
+            c_maxev = e1 > c_maxev ? e1 : c_maxev; c_sumev += e1; c_nev++; c_def += hit == 2;
+            c_g += tG1 - tG0; c_gmax = max(c_gmax, tG1 - tG0);
         }
         const long long t1 = clock64();
-        grid.sync();
+        rb_grid_barrier(P.bar, bar_target);
         const long long t2 = clock64();
-        // ---- identical bookkeeping in every CTA (only CTA 0 writes the global results)
-        int ft = -1, win = 0;
+        // ---- identical bookkeeping in every CTA (only CTA 0 writes the global tables)
+        int ft = -1, win = 0, hnew = -1;
         bool mine = false;
         if (tid < M && pos[tid] < len[tid] && cur[tid] == rmin) {
             mine = true;
             win = min(L, len[tid] - pos[tid]);
-            int unk = win;                                     // first position left untested (result 2)
-#pragma unroll
-            for (int q4 = RB_LMAX / 16 - 1; q4 >= 0; q4--) {
-                const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(res + tid * RB_LMAX) + q4);
-                const unsigned wds[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int q = 3; q >= 0; q--)
-#pragma unroll
-                    for (int bb = 3; bb >= 0; bb--) {
-                        const int idx = q4 * 16 + q * 4 + bb;
-                        const unsigned v = (wds[q] >> (8 * bb)) & 0xff;
-                        if (idx < win && v == 1) ft = idx;
-                        if (idx < win && v == 2) unk = idx;
-                    }
-            }
+            const u64 hm = __ldcg(hitmin + buf * 64 + tid);
+            const int unk = min(__ldcg(unkmin + buf * 64 + tid), win);   // first position left untested
+            if (hm != ~0ull) { ft = (int)(hm >> 32); hnew = (int)(unsigned)hm; }
             if (ft >= 0 && unk < ft) ft = -1;                  // an untested event precedes the first hit
             if (ft < 0) win = unk;                             // only the tested prefix is final
         }
-        if (tid == 0) s_newtop = 0;
-        if (tid < 64) { s_nfin[tid] = 0; s_base[tid] = 0; }
-        __syncthreads();
-        if (mine && ft >= 0 && rmin + 1 > rtop) s_newtop = 1;
-        __syncthreads();
-        if (s_newtop) {                                        // open the shared-memory row of round rmin+1
+        if (__syncthreads_or(mine && ft >= 0 && rmin + 1 > rtop)) {   // open the shared-memory row of round rmin+1
             rtop = rmin + 1;
-            if (tid < 64) Wl[rtop & (RB_WR - 1)][tid] = -1;
+            if (tid < 64) { Wl[rtop & (RB_WR - 1)][tid] = -1; Wls[rtop & (RB_WR - 1)][tid] = 0; }
             if (rtop >= P.Rcap && tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -5);
+            __syncthreads();
         }
-        __syncthreads();
-        if (mine) {
-            const int c = tid, o = off[c] + pos[c];
-            const int nfinal = ft >= 0 ? ft : win;
-            s_nfin[c] = nfinal; s_base[c] = o;
-            pos[c] += nfinal;
-            if (ft >= 0) {
-                const int hnew = P.cev[o + ft];
-                cur[c] = rmin + 1;
-                if (rmin + 1 < P.Rcap) {
-                    Wl[(rmin + 1) & (RB_WR - 1)][c] = hnew;
-                    if (lead) P.Wf[(size_t)(rmin + 1) * M + c] = hnew;
+        if (tid < 64) {
+            int nfinal = 0, o = 0;
+            if (mine) {
+                const int c = tid;
+                o = off[c] + pos[c];
+                nfinal = ft >= 0 ? ft : win;
+                if (ft >= 0) {
+                    cur[c] = rmin + 1;
+                    if (rmin + 1 < P.Rcap) {
+                        Wl[(rmin + 1) & (RB_WR - 1)][c] = hnew;
+                        Wls[(rmin + 1) & (RB_WR - 1)][c] = cmin_s[c] + pos[c] + ft;
+                        if (lead) P.Wf[(size_t)(rmin + 1) * M + c] = hnew;
+                    }
                 }
+                pos[c] += nfinal;
             }
+            s_nfin[tid] = nfinal; s_base[tid] = o;
+            if (lead) { hitmin[(buf ^ 1) * 64 + tid] = ~0ull; unkmin[(buf ^ 1) * 64 + tid] = 0x7fffffff; }
         }
         __syncthreads();
-        if (lead)                                              // final rounds of the events before the first hit
-            for (int i = tid; i < M * RB_LMAX; i += blockDim.x) {
-                const int c = i / RB_LMAX, j = i % RB_LMAX;
-                if (j < s_nfin[c]) P.round[P.cev[s_base[c] + j]] = rmin;
-            }
-        __syncthreads();
-        c_eval += t1 - t0; c_sync += t2 - t1; c_upd += clock64() - t2; c_steps++;
+        // final rounds of the events before the first hit, spread over the CTAs
+        for (int i = blockIdx.x + gridDim.x * tid; i < M * RB_LMAX; i += gridDim.x * blockDim.x) {
+            const int c = i / RB_LMAX, j = i % RB_LMAX;
+            if (j < s_nfin[c]) P.round[P.cev[s_base[c] + j]] = rmin;
+        }
+        const long long t3 = clock64();
+        c_t[0] += tA0 - t0; c_t[1] += tA1 - tA0; c_t[2] += tS1 - tA1; c_t[3] += t1 - tS1; c_t[4] += t2 - t1; c_t[5] += t3 - t2;
+        c_steps++;
     }
     if (P.dbg && lane == 0) {
-        atomicMax((unsigned long long *)P.dbg + 5, (unsigned long long)c_maxev);
-        atomicAdd((unsigned long long *)P.dbg + 6, (unsigned long long)c_miss);
-        atomicAdd((unsigned long long *)P.dbg + 7, (unsigned long long)c_sumev);
-        atomicAdd((unsigned long long *)P.dbg + 13, (unsigned long long)c_nev);
+        atomicMax((unsigned long long *)P.dbg + 8, (unsigned long long)c_maxev);
+        atomicAdd((unsigned long long *)P.dbg + 9, (unsigned long long)c_miss);
+        atomicAdd((unsigned long long *)P.dbg + 10, (unsigned long long)c_sumev);
+        atomicAdd((unsigned long long *)P.dbg + 11, (unsigned long long)c_nev);
+        atomicAdd((unsigned long long *)P.dbg + 12, (unsigned long long)c_def);
+        atomicAdd((unsigned long long *)P.dbg + 13, (unsigned long long)c_g);
+        atomicMax((unsigned long long *)P.dbg + 14, (unsigned long long)c_gmax);
     }
-    if (P.dbg && lane == 0 && warp == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
-        unsigned long long *o = (unsigned long long *)P.dbg + (blockIdx.x == 0 ? 0 : 8);
-        atomicAdd(&o[0], (unsigned long long)c_eval); atomicAdd(&o[1], (unsigned long long)c_sync);
-        atomicAdd(&o[2], (unsigned long long)c_upd); atomicAdd(&o[3], (unsigned long long)c_nev);
-        atomicAdd(&o[4], (unsigned long long)c_steps);
+    if (P.dbg && lane == 0 && warp == 0 && blockIdx.x == 0) {
+        unsigned long long *o = (unsigned long long *)P.dbg;
+        for (int i = 0; i < 6; i++) atomicAdd(&o[i], (unsigned long long)c_t[i]);
+        atomicAdd(&o[6], (unsigned long long)c_steps);
     }
     if (lead && tid == 0 && P.n > 0) P.scal[SC_MAX_ROUND] = rtop;
 }
