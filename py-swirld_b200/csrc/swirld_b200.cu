@@ -513,14 +513,16 @@ int sw_decide_fame(sw_engine *e, int32_t *new_c_out, int cap) {
     if (e->n_divided == 0) return fail(e, SW_E_ARG, "decide_fame: no witnesses yet (max() of an empty dict, swirld.py:225)");
     FameParams P{};
     P.M = e->M; P.Rcap = e->Rcap; P.C = e->C; P.W = e->d_W; P.S = e->d_S; P.famous = e->d_famous;
-    P.famous_ev = e->d_famous_ev; P.consensus = e->d_consensus; P.done = e->d_done; P.rem = e->d_rem; P.V = e->d_V;
+    P.famous_ev = e->d_famous_ev; P.consensus = e->d_consensus; P.done = e->d_done; P.rem = e->d_rem;
     P.coin = e->d_coin; P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.newc = e->d_newc; P.scal = e->d_scal;
     {
         Span sp(e, 1);
-        k_fame<<<1, 1024, 0, e->stream>>>(P);
+        k_fame_begin<<<1, 32, 0, e->stream>>>(P);
+        k_fame_rounds<<<2 * e->n_sm, 256, 0, e->stream>>>(P);
+        k_fame_finish<<<1, 1024, 0, e->stream>>>(P);
         CK(cudaGetLastError());
     }
-    e->stats.kernel_launches += 1;
+    e->stats.kernel_launches += 3;
     CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     fold_spans(e);

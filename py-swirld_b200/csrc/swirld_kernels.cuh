@@ -24,7 +24,7 @@ typedef long long i64;
 
 #define SW_WC 16             // rounds of the witness table cached in shared memory
 
-enum { SC_MAX_ROUND = 0, SC_ERR = 1, SC_NEWC = 2, SC_BATCH = 3, SC_NSEG = 4, SC_COUNT = 8 };
+enum { SC_MAX_ROUND = 0, SC_ERR = 1, SC_NEWC = 2, SC_BATCH = 3, SC_NSEG = 4, SC_MAXC = 5, SC_COUNT = 8 };
 
 struct DivParams {
     int M, first, n, Rcap;
@@ -113,11 +113,14 @@ __global__ void __launch_bounds__(256) k_strong(StrongParams P) {
 }
 
 // ---------------------------------------------------------------- K3: decide_fame
-// One CTA; voter rounds are a true sequential dependency (votes of round r_ read the
-// votes of round r_-1), candidates are independent: one thread per undecided witness
-// slot (r, member), looping over the <= M voters of the round held in shared memory.
-// V[r][mx] = mask over voter members "voted True on witness (r,mx)" in the previous
-// voter round (the only part of swirld.py:59 `votes` that is ever read again).
+// Every undecided witness x = (r, mx) is an independent recurrence over the voter rounds
+// r_ = r+1, r+2, ...: the votes of round r_ on x read only the votes of round r_-1 on x
+// (swirld.py:243-272).  So the candidate rounds run side by side, one CTA per round r, four
+// threads per witness (each covers a quarter of the <= 64 voters of a round), and a CTA stops as
+// soon as all of its witnesses are decided (2-4 voter rounds, unless coin rounds are needed).
+// The vote mask of x lives in registers; the voter rows (W, S, coin of round r_) are staged in
+// shared memory one round ahead.  k_fame_begin finds max_c (swirld.py:226-228), k_fame_finish
+// collects the rounds that reached consensus in ascending order (swirld.py:274-276).
 struct FameParams {
     int M, Rcap, C;
     const int32_t *W;        // [Rcap][M]
@@ -127,7 +130,6 @@ struct FameParams {
     uint8_t *consensus;      // [Rcap]
     uint8_t *done;           // [Rcap] scratch
     int32_t *rem;            // [Rcap] scratch: undecided witnesses of the round
-    u64 *V;                  // [Rcap][M] scratch
     const uint8_t *coin;     // [Rcap][M], written by k_strong
     const i64 *stake;
     i64 tot2;
@@ -136,34 +138,31 @@ struct FameParams {
     int32_t *scal;
 };
 
-__global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
-    // voter rows are double-buffered: the row of round r_+1 is fetched while r_ votes
+__global__ void k_fame_begin(FameParams P) {                    // one warp
+    const int lane = threadIdx.x;
+    int mc = max(P.scal[SC_MAXC], 0);                           // consensus only grows: resume from the last answer
+    for (;;) {
+        const int r = mc + lane;
+        const bool open = r >= P.Rcap || !P.consensus[r];
+        const unsigned b = __ballot_sync(0xffffffffu, open);
+        if (b) { mc += __ffs(b) - 1; break; }
+        mc += 32;
+    }
+    if (lane == 0) { P.scal[SC_MAXC] = min(mc, P.Rcap); P.scal[SC_NEWC] = 0; }
+}
+
+__global__ void __launch_bounds__(256) k_fame_rounds(FameParams P) {
     __shared__ u64 sv[2][64];
     __shared__ i64 vsum[2][64];
     __shared__ i64 stake_s[64];
     __shared__ int vw[2][64];
     __shared__ int vcoin[2][64];
-    __shared__ int s_maxc, s_lo2[2];
     const int tid = threadIdx.x, M = P.M;
     const int max_r = P.scal[SC_MAX_ROUND];                     // swirld.py:225
+    const int max_c = P.scal[SC_MAXC];
     if (tid < 64) stake_s[tid] = tid < M ? P.stake[tid] : 0;
-    if (tid == 0) {
-        int mc = 0;
-        while (mc < P.Rcap && P.consensus[mc]) mc++;            // swirld.py:226-228
-        s_maxc = mc;
-        P.scal[SC_NEWC] = 0;
-    }
-    __syncthreads();
-    const int max_c = s_maxc;
-    if (max_r < 0) return;
-    for (int r = max_c + tid; r <= max_r; r += 1024) {
-        P.done[r] = 0;
-        int cnt = 0;
-        if (!P.consensus[r])
-            for (int m = 0; m < M; m++)
-                if (P.W[(size_t)r * M + m] >= 0 && P.famous[(size_t)r * M + m] < 0) cnt++;
-        P.rem[r] = cnt;
-    }
+    const int mx = tid >> 2, q = tid & 3, mq0 = q * 16;
+    const unsigned qmask = 0xFu << (tid & 28);
     auto load_voters = [&](int r_, int buf) {                   // threads 0..63
         const int w = (tid < M && r_ <= max_r) ? P.W[(size_t)r_ * M + tid] : -1;
         vw[buf][tid] = w;
@@ -172,42 +171,22 @@ __global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
         vcoin[buf][tid] = (tid < M && r_ <= max_r) ? P.coin[(size_t)r_ * M + tid] : 0;   // swirld.py:272
         vsum[buf][tid] = wsum(s, P.unit, stake_s);
     };
-    if (tid < 2) s_lo2[tid] = max_c;
-    if (tid < 64) load_voters(max_c + 1, (max_c + 1) & 1);
-    __syncthreads();
-    // warps 0-1 fetch the next round's voters and advance the window; warps 2-31 vote:
-    // 4 threads share one undecided witness (r, mx), each covers a quarter of the voters
-    const int vt = tid - 64;                                    // voting thread id, < 0 for the fetch warps
-    const int q = tid & 3, mq0 = q * 16;
-    const unsigned qmask = 0xFu << (threadIdx.x & 28);
-    for (int r_ = max_c + 1; r_ <= max_r; ++r_) {               // iter_voters, swirld.py:238-241
-        const int buf = r_ & 1;
-        if (tid < 64) load_voters(r_ + 1, buf ^ 1);             // prefetch the next round's voters
-        // first round that may still hold an undecided witness.  The value used now was
-        // computed during the previous iteration (so it may lag: a harmless superset); the
-        // next one is computed here while this round votes.
-        const int lo = s_lo2[buf];
-        if (tid == 32) {
-            int nlo = lo;
-            while (nlo < r_ && P.rem[nlo] == 0) nlo++;
-            s_lo2[buf ^ 1] = nlo;
+    for (int r = max_c + blockIdx.x; r <= max_r; r += gridDim.x) {   // iter_undetermined, :231-236
+        __syncthreads();                                         // (shared buffers of the previous round are free)
+        const size_t slot = (size_t)r * M + mx;
+        int x = -1;
+        bool live = false;
+        if (!P.consensus[r] && mx < M) {
+            x = P.W[slot];
+            live = x >= 0 && P.famous[slot] < 0;
         }
-        const int nslots = (r_ - lo) * M;
-        for (int base = 0; base < nslots && vt >= 0; base += 240) {   // iter_undetermined, :231-236
-            const int i = base + (vt >> 2);
-            bool live = i < nslots;
-            int r = 0, mx = 0, x = -1;
-            size_t slot = 0;
-            u64 pv = 0;
-            if (live) {         // four independent loads (one memory latency, not a chain of four)
-                r = lo + i / M; mx = i % M;
-                slot = (size_t)r * M + mx;
-                const int cons = P.consensus[r];
-                x = P.W[slot];
-                const int fam = P.famous[slot];
-                pv = P.V[slot];
-                live = !cons && x >= 0 && fam < 0;
-            }
+        bool any_decided = false;
+        u64 pv = 0;
+        if (tid < 64) load_voters(r + 1, (r + 1) & 1);
+        int alive = __syncthreads_or(live);
+        for (int r_ = r + 1; r_ <= max_r && alive; ++r_) {      // iter_voters, swirld.py:238-241
+            const int buf = r_ & 1;
+            if (tid < 64) load_voters(r_ + 1, buf ^ 1);         // the next round's voters, one round ahead
             const int d = r_ - r;
             const u64 prev = d > 1 ? pv : 0ull;
             const bool coin_round = (d % P.C) == 0;
@@ -238,23 +217,39 @@ __global__ void __launch_bounds__(1024, 1) k_fame(FameParams P) {
             mlo |= __shfl_xor_sync(qmask, mlo, 2); mhi |= __shfl_xor_sync(qmask, mhi, 2);
             decided = max(decided, __shfl_xor_sync(qmask, decided, 1));
             decided = max(decided, __shfl_xor_sync(qmask, decided, 2));
-            if (live && q == 0) {
-                if (decided >= 0) {
-                    P.famous[slot] = (int8_t)decided;
-                    P.famous_ev[x] = (int8_t)decided;
-                    P.done[r] = 1;
-                    atomicSub(&P.rem[r], 1);
-                } else P.V[slot] = ((u64)mhi << 32) | mlo;
+            pv = ((u64)mhi << 32) | mlo;
+            if (live && decided >= 0) {
+                if (q == 0) { P.famous[slot] = (int8_t)decided; P.famous_ev[x] = (int8_t)decided; }
+                live = false; any_decided = true;
             }
+            alive = __syncthreads_or(live);                     // (also: the staged voters are complete)
         }
+        const int left = __syncthreads_count(live && q == 0);
+        const int dn = __syncthreads_or(any_decided);
+        if (tid == 0) { P.rem[r] = left; P.done[r] = dn ? 1 : 0; }
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_fame_finish(FameParams P) {   // swirld.py:274-276
+    __shared__ int wsum_s[32], s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int max_r = P.scal[SC_MAX_ROUND], max_c = P.scal[SC_MAXC];
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int r0 = max_c; r0 <= max_r; r0 += 1024) {
+        const int r = r0 + tid;
+        const bool hit = r <= max_r && P.done[r] && P.rem[r] == 0;
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) wsum_s[warp] = __popc(b);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; w++) before += wsum_s[w];
+        if (hit) { P.newc[before + __popc(b & ((1u << lane) - 1))] = r; P.consensus[r] = 1; }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 32; w++) t += wsum_s[w]; s_base += t; }
         __syncthreads();
     }
-    if (tid == 0) {                                              // swirld.py:274-276
-        int cnt = 0;
-        for (int r = max_c; r <= max_r; r++)
-            if (P.done[r] && P.rem[r] == 0) { P.newc[cnt++] = r; P.consensus[r] = 1; }
-        P.scal[SC_NEWC] = cnt;
-    }
+    if (tid == 0) P.scal[SC_NEWC] = s_base;
 }
 
 // ---------------------------------------------------------------- K4: find_order
