@@ -18,10 +18,14 @@ Trace: generator G1 (reference-sim gossip), seed 1 + rank.
             engine, appends each chunk from pinned host memory (H2D inside the timed
             region), runs divide_rounds + decide_fame per chunk and reads back
             round / witness / famous for all events (D2H inside the timed region).
-`roofline`: the dominant kernel k_divide_levels (level walker: can_see + rounds; its
-            counting-sort helpers and k_strong are bracketed with it), algorithmic bytes
-            B(M) = 12M + 12 + 5 + M/8 per event over its mean
-            launch duration, against MEASURED_PEAKS.json hbm_gbs.
+`roofline`: the dominant kernel k_rounds_batch (round numbers of a chunk on the whole GPU, one
+            cooperative launch per divide_rounds call): algorithmic bytes 4M + 8 + 5 + M/8 per
+            event (read the event's can_see row, p0 and creator; write round, witness flag and
+            seen-mask: SURVEY.md section 8d's B(M) minus the can_see part B1(M), plus the row
+            read that a separate kernel cannot avoid) over its mean launch duration (CUDA
+            events on the engine's stream), against MEASURED_PEAKS.json hbm_gbs.
+`roofline_can_see`: the same for the can_see kernel family k_cs_* (SURVEY.md section 8d's
+            B1(M) = 12M + 12 bytes per event), the bandwidth-bound part of the path.
 `cpu_baseline` / --impl reference: the reference is pure Python and cannot travel to
             the GPU box, so the CPU arm is the literal C restatement oracle/
             (kind "port"), single-threaded like the reference (README.md:27-28).
@@ -54,13 +58,25 @@ WORKLOADS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_divide_levels launch at c3 (65536 events), from
-# the committed ncu --set full capture profiles/r01_k_divide_levels_ncu_full.md
-WALKER_DRAM_BYTES_PER_LAUNCH = 2365952 + 2083072
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at c3 (65536 events), from the committed
+# ncu --set full captures under profiles/ (see profiles/README.md)
+ROUNDS_DRAM_BYTES_PER_LAUNCH = 18675712 + 1536        # k_rounds_batch
+WALKER_DRAM_BYTES_PER_LAUNCH = 2365952 + 2083072      # k_divide_levels (SW_DIVIDE_IMPL=4)
 
 
 def algorithmic_bytes_per_event(M):
+    """divide_rounds + decide_fame combined."""
     return 12 * M + 12 + 5 + M / 8.0
+
+
+def can_see_bytes_per_event(M):
+    """read two parent rows, write one, read p0/p1/creator."""
+    return 12 * M + 12
+
+
+def rounds_bytes_per_event(M):
+    """k_rounds_batch: read row(h), p0, creator; write round, witness flag, seen-mask."""
+    return 4 * M + 8 + 5 + M / 8.0
 
 
 def load_peaks():
@@ -253,10 +269,19 @@ def bench_ours(args, wl, rank, world, local_rank):
         eng.flush_l2()
         eng.sync()
         t0 = time.perf_counter()
-        for first, cnt in sched:
+
+        def feed(i):
+            first, cnt = sched[i]
             s = slice(first, first + cnt)
             eng.append(pin["p0"][s], pin["p1"][s], pin["creator"][s], pin["t"][s], pin["sig"][s])
+
+        # the caller's software pipeline: chunk i+1 is validated and copied (sw_append: host checks +
+        # asynchronous H2D) while the kernels of chunk i run; sw_decide_fame is the synchronising call
+        feed(0)
+        for i, (first, cnt) in enumerate(sched):
             eng.divide_rounds(first, cnt)
+            if i + 1 < len(sched):
+                feed(i + 1)
             eng.decide_fame()
         lib, h = eng._lib, eng._h
         import ctypes as C
@@ -310,10 +335,15 @@ def bench_ours(args, wl, rank, world, local_rank):
         ms_div = st1["ms_divide_rounds"] - st0["ms_divide_rounds"]
         ms_fame = st1["ms_decide_fame"] - st0["ms_decide_fame"]
         n_div_launch = len(sched) * args.steps
-        bpe = algorithmic_bytes_per_event(M)
-        # k_divide + k_strong are bracketed together by ms_divide_rounds; k_strong is the
-        # small witness-only pass (see profiles/ for the split)
-        achieved = (N * args.steps * bpe) / (ms_div * 1e-3) / 1e9
+        ms_cs = st1["ms_can_see"] - st0["ms_can_see"]
+        ms_rk = st1["ms_rounds_kernel"] - st0["ms_rounds_kernel"]
+        impl = os.environ.get("SW_DIVIDE_IMPL", "5")
+        batch = impl not in ("3", "4")
+        bpe = rounds_bytes_per_event(M) if batch else algorithmic_bytes_per_event(M)
+        ms_dom = ms_rk if ms_rk > 0 else ms_div
+        achieved = (N * args.steps * bpe) / (ms_dom * 1e-3) / 1e9
+        cs_achieved = (N * args.steps * can_see_bytes_per_event(M)) / (ms_cs * 1e-3) / 1e9 if ms_cs > 0 else None
+        path_achieved = (N * args.steps * algorithmic_bytes_per_event(M)) / ((ms_div + ms_fame) * 1e-3) / 1e9
         value = whole_job_rate(world, N, args.steps, dev_ms_max)
         e2e_value = whole_job_rate(world, N, e2e_steps, e2e_ms_max)
         # CPU baseline next to it: one pass of the oracle port on the box's host cores
@@ -328,25 +358,39 @@ def bench_ours(args, wl, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "events/s",
                     "h2d_bytes_per_step": int(N * (4 * 4 + 8 + 64)), "d2h_bytes_per_step": int(N * 6 + 64 * len(sched)),
                     "ms_per_step": e2e_ms_max / e2e_steps,
-                    "what": "reset + per chunk: sw_append (pinned host -> HBM) + sw_divide_rounds + sw_decide_fame; "
-                            "then round/witness/famous of every event back to pinned host"},
+                    "what": "reset + per chunk: sw_append (host checks, pinned host -> HBM) + sw_divide_rounds + "
+                            "sw_decide_fame, the append of chunk i+1 issued before the decide_fame of chunk i so that "
+                            "it overlaps the kernels; then round/witness/famous of every event back to pinned host"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_divide_levels (level walker: can_see rows + rounds + witnesses; "
-                                                   "one launch per chunk, bracketed with k_lvl_* and k_strong)",
+            "roofline": {"bound": "hbm",
+                         "kernel": ("k_rounds_batch (round numbers of a chunk: one cooperative launch per divide_rounds "
+                                    "call, one grid-wide step per round)") if batch else
+                                   "k_divide_levels (level walker: can_see rows + rounds + witnesses)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": WALKER_DRAM_BYTES_PER_LAUNCH if (M == 64 and K == 65536) else None,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one "
-                                           "k_divide_levels launch (profiles/r01_k_divide_levels_ncu_full.md)",
+                         "traffic": ((ROUNDS_DRAM_BYTES_PER_LAUNCH if batch else WALKER_DRAM_BYTES_PER_LAUNCH)
+                                     if (M == 64 and K == 65536) else None),
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                                           "(profiles/README.md)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_event": bpe, "events_per_launch": K,
-                         "ms_per_launch": ms_div / n_div_launch,
-                         "note": "latency/issue-bound, not HBM-bound: one CTA walks ~53.7k dependent levels per 1M "
-                                 "events at M=64 (cycle accounting: profiles/, tools/walker_cycles.py)"},
+                         "ms_per_launch": ms_dom / n_div_launch,
+                         "note": ("latency-bound, not HBM-bound: the depth of the computation is the number of rounds "
+                                  "(one grid barrier pair per round, ~1449 rounds per 1M events at M=64); cycle "
+                                  "accounting in profiles/ and tools/rounds_cycles.py") if batch else
+                                 "latency/issue-bound: one CTA walks ~53.7k dependent levels per 1M events at M=64"},
+            "roofline_can_see": None if cs_achieved is None else {
+                "bound": "hbm", "kernel": "k_cs_local + k_cs_collect + k_cs_boundary + k_cs_fix (blocked max-plus scan)",
+                "achieved": cs_achieved, "peak": peak, "unit": "GB/s", "frac": cs_achieved / peak,
+                "algorithmic_bytes_per_event": can_see_bytes_per_event(M), "ms_per_step": ms_cs / args.steps,
+                "note": "the resident leg scans all appended events in the first divide_rounds call of a step"},
+            "roofline_path": {"bound": "hbm", "what": "all kernels of divide_rounds + decide_fame, SURVEY.md 8d B(M)",
+                              "achieved": path_achieved, "peak": peak, "unit": "GB/s", "frac": path_achieved / peak,
+                              "algorithmic_bytes_per_event": algorithmic_bytes_per_event(M)},
             "kernel_ms_per_step": {"divide_rounds": ms_div / args.steps, "decide_fame": ms_fame / args.steps,
-                                   "can_see_scan": (st1["ms_can_see"] - st0["ms_can_see"]) / args.steps,
+                                   "can_see_scan": ms_cs / args.steps, "rounds_kernel": ms_rk / args.steps,
                                    "wall": wall_ms_max / args.steps},
-            "impl": {"divide": os.environ.get("SW_DIVIDE_IMPL", "4 (levels)"),
-                     "can_see": os.environ.get("SW_CANSEE_IMPL", "fused")},
+            "impl": {"divide": {"5": "5 (round batch)", "4": "4 (level walker)", "3": "3 (per-event flags)"}.get(impl, impl),
+                     "can_see": "scan" if batch else os.environ.get("SW_CANSEE_IMPL", "fused")},
             "cpu_baseline": {"value": n_cpu / s_cpu, "unit": "events/s", "cores": 1, "kind": "port",
                              "sample": "full trace (%d events), oracle/swirld_oracle.c single thread on a host with %d cpus"
                                        % (n_cpu, os.cpu_count())},

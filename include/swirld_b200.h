@@ -42,8 +42,8 @@ typedef struct sw_engine sw_engine;
 /* Cumulative counters since sw_create / sw_reset (device times from CUDA events
  * recorded on the engine's stream around the kernels of each call). */
 typedef struct sw_stats_t {
-    double ms_divide_rounds;   /* k_divide (+ k_strong) */
-    double ms_decide_fame;     /* k_fame */
+    double ms_divide_rounds;   /* every kernel of sw_divide_rounds (can_see scan, rounds, witnesses, k_strong) */
+    double ms_decide_fame;     /* k_fame_* */
     double ms_find_order;      /* k_order_* */
     double ms_can_see;         /* subset of ms_divide_rounds spent in a stand-alone can_see kernel, 0 if fused */
     int64_t kernel_launches;   /* kernels of this library launched */
@@ -51,6 +51,8 @@ typedef struct sw_stats_t {
     int64_t d2h_bytes;
     int64_t events;            /* events appended */
     int64_t events_divided;    /* events through divide_rounds */
+    double ms_rounds_kernel;   /* subset of ms_divide_rounds spent in the round-number kernel itself
+                                  (k_rounds_batch; k_divide_levels with SW_DIVIDE_IMPL=4) */
 } sw_stats_t;
 
 /* Node.__init__ state (swirld.py:38-72): M members, integer stake per member
@@ -70,7 +72,11 @@ const char *sw_last_error(const sw_engine *e);   /* e may be NULL: last create e
  * p0/p1 = self/other parent index (-1,-1 for a root: ev.p == ()), creator,
  * t = Event.t (swirld.py:91), sig = Event.s, 64 bytes each (swirld.py:92).
  * Checks what is_valid_event checks on the graph shape (swirld.py:104-108) and
- * the fork-free contract; copies the columns to the device. */
+ * the fork-free contract; copies the columns to the device.  The copies run on the
+ * engine's copy stream beside the kernels of earlier calls: when the columns are in
+ * page-locked host memory they must stay unchanged until the next synchronising call
+ * (sw_decide_fame, sw_find_order, sw_sync, any sw_get_*); pageable memory is staged
+ * before the call returns. */
 int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1,
               const int32_t *creator, const double *t, const uint8_t *sig);
 

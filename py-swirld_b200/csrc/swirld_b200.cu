@@ -33,14 +33,17 @@ struct sw_engine {
     i64 tot = 0;
     std::vector<i64> h_stake;
     // host mirrors for validation / views
-    std::vector<int32_t> h_creator, h_height, h_head, h_count, h_seq_stage;
+    std::vector<int32_t> h_creator, h_head, h_count;
+    int32_t *h_height = nullptr, *h_seq = nullptr;   // pinned, cap entries: sources of asynchronous copies
+    cudaStream_t copy_stream = nullptr;              // sw_append's copies run beside the kernels of earlier chunks
+    cudaEvent_t ev_append = nullptr;
     int n_events = 0, n_divided = 0, n_tx = 0;
     // device columns
     int32_t *d_p0 = nullptr, *d_p1 = nullptr, *d_creator = nullptr, *d_seq = nullptr, *d_height = nullptr;
     int32_t *d_hist = nullptr, *d_cursor = nullptr, *d_order = nullptr, *d_gpos = nullptr, *d_lvl_start = nullptr;
     GDesc *d_gdesc = nullptr;
     long long *d_dbg = nullptr;
-    int divide_impl = 4;          // 5 = round-batch on the whole GPU, 4 = level walker, 3 = per-event flags
+    int divide_impl = 5;          // 5 = round-batch on the whole GPU (default), 4 = level walker, 3 = per-event flags
     int n_sm = 0;
     int32_t *d_Wf = nullptr, *d_cev = nullptr, *d_rbmeta = nullptr, *d_rbtot = nullptr, *d_gchain = nullptr;   // round-batch state
     ulonglong2 *d_sc = nullptr;
@@ -126,6 +129,7 @@ void fold_spans(sw_engine *e) {
             else if (s.cat == 1) e->stats.ms_decide_fame += ms;
             else if (s.cat == 2) e->stats.ms_find_order += ms;
             else if (s.cat == 3) { e->stats.ms_can_see += ms; e->stats.ms_divide_rounds += ms; }
+            else if (s.cat == 4) e->stats.ms_rounds_kernel += ms;
         }
         e->pool.push_back(s.a); e->pool.push_back(s.b);
     }
@@ -186,7 +190,13 @@ template <int NC, bool UNIT, bool ROWS, bool FULL>
 int launch_levels4(sw_engine *e, const Div4Params &Q) {
     const size_t smem = sizeof(LvSmem<NC, ROWS>);
     CK(cudaFuncSetAttribute(k_divide_levels<NC, UNIT, ROWS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_divide_levels<NC, UNIT, ROWS, FULL><<<1, LV_THREADS, smem, e->stream>>>(Q);
+    {
+        cudaEvent_t a = get_event(e), b = get_event(e);
+        cudaEventRecord(a, e->stream);
+        k_divide_levels<NC, UNIT, ROWS, FULL><<<1, LV_THREADS, smem, e->stream>>>(Q);
+        cudaEventRecord(b, e->stream);
+        e->spans.push_back(TimedSpan{a, b, 4});
+    }
     CK(cudaGetLastError());
     return 0;
 }
@@ -274,7 +284,13 @@ int divide_round_batch(sw_engine *e, const DivParams &D) {
     k_rb_scatter<<<blocks, 256, 0, e->stream>>>(R);
     CK(cudaGetLastError());
     void *args[] = {(void *)&R};
-    CK(cudaLaunchCooperativeKernel((void *)k_rounds_batch<NC, UNIT>, dim3(grid), dim3(RB_THREADS), args, 0, e->stream));
+    {
+        cudaEvent_t a = get_event(e), b = get_event(e);
+        cudaEventRecord(a, e->stream);
+        CK(cudaLaunchCooperativeKernel((void *)k_rounds_batch<NC, UNIT>, dim3(grid), dim3(RB_THREADS), args, 0, e->stream));
+        cudaEventRecord(b, e->stream);
+        e->spans.push_back(TimedSpan{a, b, 4});
+    }
     k_rb_tail<<<blocks, 256, 0, e->stream>>>(R);
     k_rb_witness<<<blocks, 256, 0, e->stream>>>(R);
     k_rb_seenmask<NC><<<(D.n + 7) / 8, 256, 0, e->stream>>>(R);
@@ -315,18 +331,21 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
     i64 per = std::min<i64>(M, (2 * e->tot) / 3 + 1);
     if (per < 1) per = 1;
     e->Rcap = (int)std::min<i64>((i64)e->cap + 2, (i64)e->cap / per + 16);
-    if (const char *impl = getenv("SW_DIVIDE_IMPL")) { int v = atoi(impl); e->divide_impl = (v == 3 || v == 5) ? v : 4; }
+    if (const char *impl = getenv("SW_DIVIDE_IMPL")) { int v = atoi(impl); e->divide_impl = (v == 3 || v == 4) ? v : 5; }
     if (const char *impl = getenv("SW_CANSEE_IMPL")) e->cansee_scan = strcmp(impl, "scan") == 0 ? 1 : 0;
     if (e->divide_impl == 3) e->cansee_scan = 0;
     if (e->divide_impl == 5) e->cansee_scan = 1;     // the round-batch kernel reads finished can_see rows
     e->h_head.assign(M, -1);
     e->h_count.assign(M, 0);
     e->h_creator.reserve(e->cap);
-    e->h_height.reserve(e->cap);
     int rc = [&]() -> int {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_append, cudaEventDisableTiming));
         const size_t cap = e->cap, RM = (size_t)e->Rcap * M;
+        CK(cudaMallocHost((void **)&e->h_height, sizeof(int32_t) * cap));
+        CK(cudaMallocHost((void **)&e->h_seq, sizeof(int32_t) * cap));
         CK(dalloc(&e->d_p0, cap)); CK(dalloc(&e->d_p1, cap)); CK(dalloc(&e->d_creator, cap)); CK(dalloc(&e->d_seq, cap));
         CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64)); CK(dalloc(&e->d_height, cap));
         CK(dalloc(&e->d_hist, cap + 2)); CK(dalloc(&e->d_cursor, cap + 2)); CK(dalloc(&e->d_order, cap));
@@ -375,6 +394,10 @@ void sw_destroy(sw_engine *e) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (e->h_scal) cudaFreeHost(e->h_scal);
     if (e->h_newc) cudaFreeHost(e->h_newc);
+    if (e->h_height) cudaFreeHost(e->h_height);
+    if (e->h_seq) cudaFreeHost(e->h_seq);
+    if (e->ev_append) cudaEventDestroy(e->ev_append);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -384,7 +407,7 @@ int sw_reset(sw_engine *e) {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     fold_spans(e);
-    e->h_creator.clear(); e->h_height.clear();
+    e->h_creator.clear();
     int rc = reset_state(e);
     memset(&e->stats, 0, sizeof e->stats);
     return rc;
@@ -426,9 +449,7 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
     const int base = e->n_events;
     // graph-shape checks of is_valid_event (swirld.py:104-108) + the fork-free contract
     std::vector<int32_t> head_save(e->h_head), count_save(e->h_count);
-    e->h_seq_stage.resize(n);
     e->h_creator.resize((size_t)base + n);
-    e->h_height.resize((size_t)base + n);
     int rc = SW_OK;
     for (int j = 0; j < n && rc == SW_OK; j++) {
         const int i = base + j, c = creator[j], a = p0[j], b = p1[j];
@@ -445,22 +466,25 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
         }
         e->h_creator[i] = c;
         e->h_head[c] = i;
-        e->h_seq_stage[j] = e->h_count[c]++;
+        e->h_seq[i] = e->h_count[c]++;
     }
     if (rc != SW_OK) {
         e->h_head = head_save; e->h_count = count_save;
-        e->h_creator.resize(base); e->h_height.resize(base);
+        e->h_creator.resize(base);
         return rc;
     }
-    CK(cudaMemcpyAsync(e->d_p0 + base, p0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_p1 + base, p1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_creator + base, creator, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_t + base, t, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_sig + (size_t)base * 64, sig, (size_t)64 * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_seq + base, e->h_seq_stage.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_height + base, e->h_height.data() + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
-    // h_seq_stage is reused by the next append: the copy above must have left the host buffer
-    CK(cudaStreamSynchronize(e->stream));
+    // The copies go to their own stream: they touch only the new rows, so they overlap the kernels of
+    // earlier chunks still running on the compute stream; later compute work waits for them.
+    cudaStream_t cs = e->copy_stream;
+    CK(cudaMemcpyAsync(e->d_p0 + base, p0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(e->d_p1 + base, p1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(e->d_creator + base, creator, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(e->d_t + base, t, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(e->d_sig + (size_t)base * 64, sig, (size_t)64 * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(e->d_seq + base, e->h_seq + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(e->d_height + base, e->h_height + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(e->ev_append, cs));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_append, 0));
     e->stats.h2d_bytes += (i64)n * (5 * 4 + 8 + 64);
     e->stats.events += n;
     e->n_events += n;
@@ -642,7 +666,7 @@ GETTER(sw_get_idx, int32_t, e->d_idx, e->n_events, 1)
 int sw_get_height(sw_engine *e, int first, int n, int32_t *out) {
     if (!e || first < 0 || n < 0 || (n > 0 && !out)) return fail(e, SW_E_ARG, "bad argument");
     if (first + n > e->n_events) return fail(e, SW_E_KEY, "sw_get_height: out of range");
-    memcpy(out, e->h_height.data() + first, sizeof(int32_t) * n);
+    memcpy(out, e->h_height + first, sizeof(int32_t) * n);
     return SW_OK;
 }
 

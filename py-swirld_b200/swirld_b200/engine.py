@@ -31,7 +31,7 @@ class SwStats(C.Structure):
     _fields_ = [("ms_divide_rounds", C.c_double), ("ms_decide_fame", C.c_double),
                 ("ms_find_order", C.c_double), ("ms_can_see", C.c_double),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("events", C.c_int64), ("events_divided", C.c_int64)]
+                ("events", C.c_int64), ("events_divided", C.c_int64), ("ms_rounds_kernel", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
