@@ -108,7 +108,7 @@ class ClockSampler:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.th.start()
@@ -325,6 +325,7 @@ def bench_ours(args, wl, rank, world, local_rank):
     e2e_steps = args.steps
     for _ in range(e2e_steps):
         e2e_ms += step_e2e()
+    st_e2e = eng.stats()              # sw_reset clears the counters: this is the last e2e step alone
     barrier()
 
     dev_ms_max, e2e_ms_max, wall_ms_max = max_over_ranks([dev_ms, e2e_ms, wall_ms], dist, "cuda")
@@ -358,6 +359,8 @@ def bench_ours(args, wl, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "events/s",
                     "h2d_bytes_per_step": int(N * (4 * 4 + 8 + 64)), "d2h_bytes_per_step": int(N * 6 + 64 * len(sched)),
                     "ms_per_step": e2e_ms_max / e2e_steps,
+                    "kernel_ms_last_step": {"divide_rounds": st_e2e["ms_divide_rounds"], "can_see_scan": st_e2e["ms_can_see"],
+                                            "rounds_kernel": st_e2e["ms_rounds_kernel"], "decide_fame": st_e2e["ms_decide_fame"]},
                     "what": "reset + per chunk: sw_append (host checks, pinned host -> HBM) + sw_divide_rounds + "
                             "sw_decide_fame, the append of chunk i+1 issued before the decide_fame of chunk i so that "
                             "it overlaps the kernels; then round/witness/famous of every event back to pinned host"},
@@ -406,7 +409,7 @@ def bench_ours(args, wl, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))

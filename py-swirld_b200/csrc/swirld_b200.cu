@@ -51,7 +51,7 @@ struct sw_engine {
     int cansee_scan = 0;          // 1 = can_see by the blocked scan k_cs_* (SW_CANSEE_IMPL=scan), 0 = fused into the walker
     int n_rowed = 0;              // events whose can_see row is complete (cansee_scan)
     uint8_t *d_exported = nullptr;
-    int32_t *d_exp_list = nullptr, *d_exp_cnt = nullptr, *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_CM = nullptr, *d_cs_carry = nullptr;
+    int32_t *d_exp_list = nullptr, *d_exp_m = nullptr, *d_exp_cnt = nullptr, *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_CM = nullptr, *d_cs_carry = nullptr;
     double *d_t = nullptr;
     uint8_t *d_sig = nullptr;
     int32_t *d_row = nullptr, *d_round = nullptr;
@@ -215,16 +215,16 @@ int cansee_scan(sw_engine *e) {
     C.B = std::min(n, n >= 200000 ? 4096 : 2048);
     C.nb = (n + C.B - 1) / C.B;
     C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.row = e->d_row;
-    C.exported = e->d_exported; C.exp_list = e->d_exp_list; C.exp_cnt = e->d_exp_cnt;
-    C.last = e->d_cs_last; C.Qtab = e->d_cs_Q; C.CM = e->d_cs_CM; C.carry = e->d_cs_carry;
+    C.exported = e->d_exported; C.exp_list = e->d_exp_list; C.exp_m = e->d_exp_m; C.exp_cnt = e->d_exp_cnt;
+    C.last = e->d_cs_last; C.Qtab = e->d_cs_Q; C.carry = e->d_cs_carry;
     CK(cudaMemsetAsync(e->d_exported + first, 0, (size_t)n, e->stream));
     CK(cudaMemsetAsync(e->d_exp_cnt, 0, sizeof(int32_t) * (size_t)C.nb, e->stream));
     cudaEvent_t a = get_event(e), b = get_event(e);
     cudaEventRecord(a, e->stream);
-    k_cs_local<NC><<<C.nb, NC * 32, 0, e->stream>>>(C);
+    k_cs_local<NC, 1><<<C.nb, NC * 32, 0, e->stream>>>(C);
     k_cs_collect<<<std::max(1, std::min(296, (n + 255) / 256)), 256, 0, e->stream>>>(C);
     k_cs_boundary<NC><<<1, 1024, 0, e->stream>>>(C);
-    k_cs_fix<NC><<<dim3((C.B + CS_FIX_EVENTS - 1) / CS_FIX_EVENTS, C.nb), 256, 0, e->stream>>>(C);
+    k_cs_local<NC, 2><<<C.nb, NC * 32, 0, e->stream>>>(C);
     cudaEventRecord(b, e->stream);
     e->spans.push_back(TimedSpan{a, b, 3});
     CK(cudaGetLastError());
@@ -350,7 +350,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64)); CK(dalloc(&e->d_height, cap));
         CK(dalloc(&e->d_hist, cap + 2)); CK(dalloc(&e->d_cursor, cap + 2)); CK(dalloc(&e->d_order, cap));
         CK(dalloc(&e->d_gpos, cap)); CK(dalloc(&e->d_lvl_start, cap + 2)); CK(dalloc(&e->d_gdesc, cap));
-        CK(dalloc(&e->d_exported, cap)); CK(dalloc(&e->d_exp_list, cap + 8192)); CK(dalloc(&e->d_exp_cnt, cap / 2048 + 4));
+        CK(dalloc(&e->d_exported, cap)); CK(dalloc(&e->d_exp_list, cap + 8192)); CK(dalloc(&e->d_exp_m, cap + 8192)); CK(dalloc(&e->d_exp_cnt, cap / 2048 + 4));
         CK(dalloc(&e->d_cs_last, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_Q, (cap / 2048 + 5) * (size_t)M));
         CK(dalloc(&e->d_cs_CM, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_carry, (size_t)64));
         CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, cap)); CK(dalloc(&e->d_rbmeta, (size_t)256));
@@ -385,7 +385,7 @@ void sw_destroy(sw_engine *e) {
     fold_spans(e);
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
-    void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_CM, e->d_cs_carry, e->d_exported, e->d_exp_list, e->d_exp_cnt, e->d_coin, e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
+    void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_CM, e->d_cs_carry, e->d_exported, e->d_exp_list, e->d_exp_m, e->d_exp_cnt, e->d_coin, e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
                     e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_V, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,

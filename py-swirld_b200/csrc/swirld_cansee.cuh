@@ -15,15 +15,15 @@
 //   B  k_cs_boundary  one CTA walks the blocks in order and finishes the few rows later
 //                     blocks depend on: the events referenced from later blocks ("exported")
 //                     and each member's last event of the block (the next block-start heads).
-//   C  k_cs_fix       every other event with a column that is not in-block is finished in
-//                     parallel.
+//   C  k_cs_local<2>  every block again, now with the final rows of its out-of-block parents (the heads
+//                     of B are preloaded): the exact recurrence, blocks in parallel.
 //
-// Finishing a row: for every member m, the out-of-block ancestor that represents it is
+// Finishing a row in B: for every member m, the out-of-block ancestor that represents it is
 //   e_m = Q[m] (member m's head at the start of the block) if h sees an in-block m-event,
 //   else PR(h)[m] (a direct out-of-block parent, possibly older than the head), else none;
-// row(h)[c] = max(PR(h)[c], max_m row(e_m)[c]) for the columns that are not in-block.  When
-// every e_m is the head Q[m] (the usual case once the block has mixed) that inner max is the
-// per-block constant CM[c] = max_m row(Q[m])[c]: one compare per column, no gathers.
+// row(h)[c] = max(PR(h)[c], max_m row(e_m)[c]) for the columns that are not in-block.  A row
+// whose out-of-block columns already show the heads themselves is final as it is (Q[c] is the
+// largest value column c can take below the block).
 //
 // (tests/test_cansee_model.py keeps an executable model of exactly this scheme against the oracle.)
 #pragma once
@@ -35,109 +35,173 @@ struct CsParams {
     int32_t *row;               // [cap][M]; rows < first are final
     uint8_t *exported;          // [cap] flags, zero on entry for [first, first+n)
     int32_t *exp_list;          // [cap]: block j's list lives at [first + j*B, ...)
+    int32_t *exp_m;             // [cap]: for a list entry that is its member's last event of the block, the member; else -1
     int32_t *exp_cnt;           // [nb]
     int32_t *last;              // [nb][M] last event of member m inside block j, -1 none
     int32_t *Qtab;              // [nb+1][M] head of member m at the start of block j
-    int32_t *CM;                // [nb][M]  column-wise max of the rows of Qtab[j][*]
     int32_t *carry;             // [M] heads before `first` (in/out: updated to the heads after the range)
 };
 
 #define CS_TILE 256
 
-// ---- A: per-block partial rows.  blockDim.x = 32*NC threads = member columns.
-template <int NC>
+// ---- A / C: the in-block recurrence, one CTA per block, blockDim.x = 32*NC threads = member columns.
+// PASS 1: partial rows (out-of-block parents are leaves).  PASS 2 (after k_cs_boundary): the exact
+// rows -- the same walk, but an out-of-block parent contributes its FINAL row: the block-start heads
+// are preloaded into the per-member cache, anything older is read from the table.
+// Per member the cache holds its latest event so far and that event's value in this thread's column;
+// in a gossip graph both parents of a new event are such "latest" events, so the walk runs out of
+// shared memory.  Two consecutive events are processed together when the second does not have the
+// first as a parent (its loads are issued before the first one's store: ~2x on the latency chain).
+template <int NC, int PASS>
 __global__ void __launch_bounds__(NC * 32) k_cs_local(CsParams P) {
     constexpr int MS = NC * 32;
     __shared__ int2 tv[MS][MS];              // [member][column]: (event, its cached value); one LDS.64
-    __shared__ int32_t sp0[CS_TILE], sp1[CS_TILE], scr[CS_TILE], scb[CS_TILE];
+    __shared__ int4 meta[CS_TILE + 2];       // (p0, p1, creator | dep << 16, creator of p1)
     const int c = threadIdx.x, M = P.M;
     const int s = P.first + blockIdx.x * P.B, e = min(s + P.B, P.first + P.n);
-    for (int m = 0; m < MS; m++) tv[m][c] = make_int2(-1, -1);   // private to this thread's column
+    __shared__ int32_t qs[MS];
+    if (PASS == 2) {
+        qs[c] = c < M ? P.Qtab[(size_t)blockIdx.x * M + c] : -1;
+        __syncthreads();
+    }
+#pragma unroll 8
+    for (int m = 0; m < MS; m++) {           // private to this thread's column
+        const int q = PASS == 2 ? qs[m] : -1;
+        const bool on = q >= 0 && c < M;
+        const int val = on ? P.row[(size_t)(on ? q : 0) * M + (on ? c : 0)] : -1;   // independent loads, no branches
+        tv[m][c] = make_int2(q, val);
+    }
     for (int t0 = s; t0 < e; t0 += CS_TILE) {
         const int tn = min(CS_TILE, e - t0);
         __syncthreads();
-        for (int i = c; i < tn; i += MS) {
-            const int a = P.p0[t0 + i], b = P.p1[t0 + i];
-            sp0[i] = a; sp1[i] = b; scr[i] = P.creator[t0 + i];
-            scb[i] = b >= 0 ? P.creator[b] : 0;
-            if (a >= P.first && a < s) P.exported[a] = 1;   // referenced from a later block
-            if (b >= P.first && b < s) P.exported[b] = 1;
+        for (int i = c; i < tn + 2; i += MS) {
+            int4 mt = make_int4(-1, -1, 1 << 16, 0);             // padding: "depends on its predecessor"
+            if (i < tn) {
+                const int a = P.p0[t0 + i], b = P.p1[t0 + i];
+                const int dep = (a == t0 + i - 1 || b == t0 + i - 1) ? 1 : 0;
+                mt = make_int4(a, b, P.creator[t0 + i] | (dep << 16), b >= 0 ? P.creator[b] : 0);
+                if (PASS == 1) {
+                    if (a >= P.first && a < s) P.exported[a] = 1;   // referenced from a later block
+                    if (b >= P.first && b < s) P.exported[b] = 1;
+                }
+            }
+            meta[i] = mt;
         }
         __syncthreads();
         if (c >= M) continue;
-        for (int i = 0; i < tn; i++) {
-            const int h = t0 + i, pa = sp0[i], pb = sp1[i], cr = scr[i], cb = scb[i];
-            int v = -1;
-            if (pa >= 0) {
-                const int2 ca = tv[cr][c], cbv = tv[cb][c];   // both cached heads at once
-                int a, b;
-                if (pa >= s) a = ca.x == pa ? ca.y : P.row[(size_t)pa * M + c];
-                else a = c == cr ? pa : -1;                  // out-of-block parent: a leaf
-                if (pb >= s) b = cbv.x == pb ? cbv.y : P.row[(size_t)pb * M + c];
-                else b = c == cb ? pb : -1;
-                v = max(a, b);
+        // One parent's contribution to column c, branch-free: the cached head of the parent's member if it
+        // IS the parent, else (pass 1) the leaf value of an out-of-block parent; `need` = a table read is due.
+        auto contrib = [&](int p, int pc, int2 cached, bool &need) -> int {
+            const bool hit = cached.x == p;
+            need = (PASS == 1 ? p >= s : p >= 0) && !hit;
+            const int leaf = (PASS == 1 && p >= 0 && p < s && c == pc) ? p : -1;
+            return hit ? cached.y : leaf;
+        };
+        int i = 0;
+        int4 m0 = meta[0];
+        while (i < tn) {
+            const int4 m1 = meta[i + 1];
+            const int h = t0 + i;
+            const int cr0 = m0.z & 0xffff, cr1 = m1.z & 0xffff;
+            if ((m1.z >> 16) == 0) {                                            // independent pair (i, i+1)
+                const int2 a0 = tv[cr0][c], b0 = tv[m0.w][c], a1 = tv[cr1][c], b1 = tv[m1.w][c];
+                const int4 m2 = meta[i + 2];
+                // (all four loads in flight before the first use: keeps them out of the branches below)
+                asm volatile("" :: "r"(a0.x), "r"(a0.y), "r"(b0.x), "r"(b0.y), "r"(a1.x), "r"(a1.y), "r"(b1.x), "r"(b1.y));
+                bool na0, nb0, na1, nb1;
+                int x0 = contrib(m0.x, cr0, a0, na0), y0 = contrib(m0.y, m0.w, b0, nb0);
+                int x1 = contrib(m1.x, cr1, a1, na1), y1 = contrib(m1.y, m1.w, b1, nb1);
+                if (na0 | nb0 | na1 | nb1) {                                    // rare: a parent that is not its member's latest event
+                    if (na0) x0 = P.row[(size_t)m0.x * M + c];
+                    if (nb0) y0 = P.row[(size_t)m0.y * M + c];
+                    if (na1) x1 = P.row[(size_t)m1.x * M + c];
+                    if (nb1) y1 = P.row[(size_t)m1.y * M + c];
+                }
+                const int v0 = c == cr0 ? h : max(x0, y0), v1 = c == cr1 ? h + 1 : max(x1, y1);
+                tv[cr0][c] = make_int2(h, v0);
+                tv[cr1][c] = make_int2(h + 1, v1);
+                P.row[(size_t)h * M + c] = v0;
+                P.row[(size_t)(h + 1) * M + c] = v1;
+                m0 = m2; i += 2;
+            } else {
+                const int2 a0 = tv[cr0][c], b0 = tv[m0.w][c];
+                asm volatile("" :: "r"(a0.x), "r"(a0.y), "r"(b0.x), "r"(b0.y));
+                bool na0, nb0;
+                int x0 = contrib(m0.x, cr0, a0, na0), y0 = contrib(m0.y, m0.w, b0, nb0);
+                if (na0 | nb0) {
+                    if (na0) x0 = P.row[(size_t)m0.x * M + c];
+                    if (nb0) y0 = P.row[(size_t)m0.y * M + c];
+                }
+                const int v0 = c == cr0 ? h : max(x0, y0);
+                tv[cr0][c] = make_int2(h, v0);
+                P.row[(size_t)h * M + c] = v0;
+                m0 = m1; i += 1;
             }
-            if (c == cr) v = h;
-            tv[cr][c] = make_int2(h, v);
-            P.row[(size_t)h * M + c] = v;
         }
     }
-    if (c < M) P.last[(size_t)blockIdx.x * M + c] = tv[c][c].x;  // member c's last event of the block
+    if (PASS == 1 && c < M) P.last[(size_t)blockIdx.x * M + c] = tv[c][c].x;  // member c's last event of the block
 }
 
-// per-block lists of the exported events
+// per-block work lists of k_cs_boundary: the exported events and each member's last event of the block
+// (entry = event, and the member whose block-end head it is, or -1)
 __global__ void k_cs_collect(CsParams P) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.n; j += gridDim.x * blockDim.x) {
-        const int x = P.first + j;
-        if (P.exported[x]) {
-            const int blk = j / P.B;
+        const int x = P.first + j, blk = j / P.B, cr = P.creator[x];
+        const bool is_last = P.last[(size_t)blk * P.M + cr] == x;
+        if (P.exported[x] || is_last) {
             const int pos = atomicAdd(&P.exp_cnt[blk], 1);
             P.exp_list[P.first + blk * P.B + pos] = x;
+            P.exp_m[P.first + blk * P.B + pos] = is_last ? cr : -1;
+            P.exported[x] = 1;
         }
     }
 }
 
-// Finish one row (one warp, lanes = columns, NC per lane).  Q/S/CMs live in shared memory:
-// Q[m] the block-start heads, S[m][c] their final rows, CMs[c] the column maxima (NULL: no fast path).
+// Finish one row (one warp, lanes = columns, NC per lane).  pr: in = the partial row, out = the final row.
+// Q[m] the block-start heads, S[m][c] their final rows (shared memory).
 template <int NC>
-__device__ __forceinline__ void cs_complete_row(const CsParams &P, int x, int lim, int lane,
-                                                const int32_t *Q, const int32_t (*S)[NC * 32], const int32_t *CMs) {
+__device__ __forceinline__ void cs_complete_row(const CsParams &P, int x, int lim, int lane, const int32_t *Q,
+                                                const int32_t (*S)[NC * 32], int (&pr)[NC]) {
     const int M = P.M;
-    int pr[NC], q[NC];
+    int q[NC];
     bool inb[NC];
-    bool all_in = true, fast = CMs != nullptr;
+    bool all_in = true, fast = true;
 #pragma unroll
     for (int j = 0; j < NC; j++) {
         const int c = lane + 32 * j;
-        pr[j] = c < M ? P.row[(size_t)x * M + c] : 0x7fffffff;     // padded columns count as in-block
+        if (c >= M) pr[j] = 0x7fffffff;                             // padded columns count as in-block
         q[j] = c < M ? Q[c] : -1;
         inb[j] = pr[j] >= lim;
         all_in &= inb[j];
-        // fast path: every member with a head is represented by exactly that head
-        fast &= inb[j] ? true : (pr[j] == q[j]);                    // covers "no head, nothing seen" (-1 == -1)
+        // every out-of-block column already shows its member's head: nothing older can add to it
+        // (the head of c is the largest value column c can take outside the block)
+        fast &= inb[j] || pr[j] == q[j];
     }
-    if (__all_sync(0xffffffffu, all_in)) return;                    // nothing outside the block: already final
+    if (__all_sync(0xffffffffu, all_in | fast)) return;
     int acc[NC];
-    if (__all_sync(0xffffffffu, fast)) {
 #pragma unroll
-        for (int j = 0; j < NC; j++) acc[j] = inb[j] ? pr[j] : max(pr[j], CMs[lane + 32 * j]);
-    } else {
+    for (int j = 0; j < NC; j++) acc[j] = pr[j];
 #pragma unroll
-        for (int j = 0; j < NC; j++) acc[j] = pr[j];
+    for (int jj = 0; jj < NC; jj++) {
+        const int cj = lane + 32 * jj;
+        // members whose chain below the block is entered at the head (h sees an in-block event of the
+        // member, or has the head itself as a parent) / at an older event (a direct out-of-block parent)
+        unsigned hm = __ballot_sync(0xffffffffu, cj < M && q[jj] >= 0 && (inb[jj] || pr[jj] == q[jj]));
+        unsigned om = __ballot_sync(0xffffffffu, cj < M && !inb[jj] && pr[jj] >= 0 && pr[jj] != q[jj]);
+        while (hm) {
+            const int m = jj * 32 + __ffs(hm) - 1;
+            hm &= hm - 1;
 #pragma unroll
-        for (int jj = 0; jj < NC; jj++) {
-            for (int l = 0; l < 32; l++) {
-                const int m = jj * 32 + l;
-                if (m >= M) break;
-                int ev = __shfl_sync(0xffffffffu, pr[jj], l);
-                const int qm = __shfl_sync(0xffffffffu, q[jj], l);
-                if (ev >= lim) ev = qm;                             // sees an in-block m-event: its chain reaches the head
-                if (ev < 0) continue;
+            for (int j = 0; j < NC; j++) acc[j] = max(acc[j], S[m][lane + 32 * j]);
+        }
+        while (om) {
+            const int l = __ffs(om) - 1;
+            om &= om - 1;
+            const int ev = __shfl_sync(0xffffffffu, pr[jj], l);
 #pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const int c = lane + 32 * j;
-                    if (c < M) acc[j] = max(acc[j], ev == qm ? S[m][c] : __ldcg(P.row + (size_t)ev * M + c));
-                }
+            for (int j = 0; j < NC; j++) {
+                const int c = lane + 32 * j;
+                if (c < M) acc[j] = max(acc[j], __ldcg(P.row + (size_t)ev * M + c));
             }
         }
     }
@@ -145,76 +209,75 @@ __device__ __forceinline__ void cs_complete_row(const CsParams &P, int x, int li
     for (int j = 0; j < NC; j++) {
         const int c = lane + 32 * j;
         if (c < M && !inb[j] && acc[j] != pr[j]) P.row[(size_t)x * M + c] = acc[j];
+        if (!inb[j]) pr[j] = acc[j];
     }
 }
 
-// ---- B: block by block, the rows later blocks depend on
+// ---- B: block by block, the rows later blocks depend on.  One CTA; per block: finish the listed rows
+// (one warp per row, the partial rows of a warp's batch are fetched together), then install the block's
+// last events as the new heads.  The next block's list is fetched while this one is processed.
+#define CS_LIST 768
 template <int NC>
 __global__ void __launch_bounds__(1024, 1) k_cs_boundary(CsParams P) {
     constexpr int MS = NC * 32;
-    __shared__ int32_t Q[MS], CMs[MS];
-    __shared__ int32_t S[MS][MS];
-    __shared__ int cnt_s;
+    __shared__ int32_t Q[MS], newq[MS];
+    __shared__ int32_t S[MS][MS], Snew[MS][MS];
+    __shared__ int32_t lst[2][CS_LIST], lstm[2][CS_LIST];
+    __shared__ int cnt_s[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = P.M;
-    if (tid < MS) Q[tid] = tid < M ? P.carry[tid] : -1;
+    if (tid < MS) { Q[tid] = tid < M ? P.carry[tid] : -1; newq[tid] = -1; }
+    if (tid == 0) cnt_s[0] = P.exp_cnt[0];
     __syncthreads();
     for (int i = tid; i < MS * MS; i += 1024) {
         const int m = i / MS, c = i % MS;
         S[m][c] = (m < M && c < M && Q[m] >= 0) ? P.row[(size_t)Q[m] * M + c] : -1;
     }
+    if (tid < min(cnt_s[0], CS_LIST)) { lst[0][tid] = P.exp_list[P.first + tid]; lstm[0][tid] = P.exp_m[P.first + tid]; }
     __syncthreads();
     for (int blk = 0; blk < P.nb; blk++) {
-        const int lim = P.first + blk * P.B;
-        int32_t *list = P.exp_list + lim;
-        if (tid < MS) {                                      // tables for k_cs_fix
-            int cm = -1;
-            for (int m = 0; m < M; m++) cm = max(cm, S[m][tid]);
-            CMs[tid] = cm;
-            if (tid < M) { P.CM[(size_t)blk * M + tid] = cm; P.Qtab[(size_t)blk * M + tid] = Q[tid]; }
+        const int buf = blk & 1, lim = P.first + blk * P.B, cnt = cnt_s[buf];
+        const int32_t *glist = P.exp_list + lim, *glm = P.exp_m + lim;
+        if (tid < M) P.Qtab[(size_t)blk * M + tid] = Q[tid];             // heads for pass 2
+        // the next block's list: loads now, shared-memory stores after this block's rows
+        int ncnt = 0, nx = -1, nm = -1;
+        if (blk + 1 < P.nb) {
+            ncnt = P.exp_cnt[blk + 1];
+            if (tid < min(ncnt, CS_LIST)) { nx = P.exp_list[lim + P.B + tid]; nm = P.exp_m[lim + P.B + tid]; }
         }
-        if (tid == 0) cnt_s = P.exp_cnt[blk];
-        __syncthreads();
-        if (tid < M) {                                       // the block's last event of every member
-            const int x = P.last[(size_t)blk * M + tid];
-            if (x >= 0 && !P.exported[x]) { P.exported[x] = 1; list[atomicAdd(&cnt_s, 1)] = x; }
+        for (int i0 = warp; i0 < cnt; i0 += 128) {                      // up to four rows per warp and trip
+            int x[4], mm[4], pr[4][NC];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + 32 * u;
+                x[u] = -1; mm[u] = -1;
+                if (i < cnt) { x[u] = i < CS_LIST ? lst[buf][i] : glist[i]; mm[u] = i < CS_LIST ? lstm[buf][i] : glm[i]; }
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const int c = lane + 32 * j;
+                    pr[u][j] = (x[u] >= 0 && c < M) ? P.row[(size_t)x[u] * M + c] : 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (x[u] < 0) continue;                                  // uniform
+                cs_complete_row<NC>(P, x[u], lim, lane, Q, S, pr[u]);
+                if (mm[u] >= 0) {                                        // the member's head after this block
+#pragma unroll
+                    for (int j = 0; j < NC; j++) if (lane + 32 * j < M) Snew[mm[u]][lane + 32 * j] = pr[u][j];
+                    if (lane == 0) newq[mm[u]] = x[u];
+                }
+            }
         }
         __syncthreads();
-        const int cnt = cnt_s;
-        for (int i = warp; i < cnt; i += 32) cs_complete_row<NC>(P, list[i], lim, lane, Q, S, CMs);
-        __syncthreads();
-        for (int i = tid; i < MS * MS; i += 1024) {          // heads for the next block
+        for (int i = tid; i < MS * MS; i += 1024) {
             const int m = i / MS, c = i % MS;
-            const int x = m < M ? P.last[(size_t)blk * M + m] : -1;
-            if (x >= 0 && c < M) S[m][c] = P.row[(size_t)x * M + c];
+            if (newq[m] >= 0) S[m][c] = Snew[m][c];
         }
+        if (tid < min(ncnt, CS_LIST)) { lst[buf ^ 1][tid] = nx; lstm[buf ^ 1][tid] = nm; }
+        if (tid == 0) cnt_s[buf ^ 1] = ncnt;
         __syncthreads();
-        if (tid < M) { const int x = P.last[(size_t)blk * M + tid]; if (x >= 0) Q[tid] = x; }
+        if (tid < MS && newq[tid] >= 0) { Q[tid] = newq[tid]; newq[tid] = -1; }
         __syncthreads();
     }
     if (tid < M) { P.carry[tid] = Q[tid]; P.Qtab[(size_t)P.nb * M + tid] = Q[tid]; }
-}
-
-// ---- C: everything else, in parallel.  grid = (tiles per block, nb), 8 warps, 512 events per CTA.
-#define CS_FIX_EVENTS 512
-template <int NC>
-__global__ void __launch_bounds__(256) k_cs_fix(CsParams P) {
-    constexpr int MS = NC * 32;
-    __shared__ int32_t Q[MS], CMs[MS];
-    __shared__ int32_t S[MS][MS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = P.M;
-    const int blk = blockIdx.y;
-    const int lim = P.first + blk * P.B, bend = min(lim + P.B, P.first + P.n);
-    const int t0 = lim + blockIdx.x * CS_FIX_EVENTS, t1 = min(t0 + CS_FIX_EVENTS, bend);
-    if (t0 >= bend) return;
-    if (tid < MS) { Q[tid] = tid < M ? P.Qtab[(size_t)blk * M + tid] : -1; CMs[tid] = tid < M ? P.CM[(size_t)blk * M + tid] : -1; }
-    __syncthreads();
-    for (int i = tid; i < MS * MS; i += 256) {
-        const int m = i / MS, c = i % MS;
-        S[m][c] = (m < M && c < M && Q[m] >= 0) ? P.row[(size_t)Q[m] * M + c] : -1;
-    }
-    __syncthreads();
-    for (int x = t0 + warp; x < t1; x += 8) {
-        if (P.exported[x]) continue;                         // finished by k_cs_boundary
-        cs_complete_row<NC>(P, x, lim, lane, Q, S, CMs);
-    }
 }

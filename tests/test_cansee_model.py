@@ -1,7 +1,7 @@
 """Executable model of the blocked can_see scan (py-swirld_b200/csrc/swirld_cansee.cuh:
 partial rows per block with out-of-block parents as leaves, block-start heads as the
-representatives of what lies below the block, column-max fast path) against the literal
-oracle, on CPU.  Covers stale other-parents, several launches and one-event launches."""
+representatives of what lies below the block for the rows later blocks depend on, then the
+exact in-block walk with the finished out-of-block rows) against the literal oracle, on CPU.  Covers stale other-parents, several launches and one-event launches."""
 import numpy as np
 import pytest
 
@@ -43,8 +43,9 @@ def scan_launch(tr, first, n, B, row, carry, stats):
             return
         q = Q[blk]
         if fast_ok and np.all(inb | (pr == q)):
-            stats["fast"] += 1
-            row[x] = np.where(inb, pr, np.maximum(pr, CM[blk]))
+            stats["fast"] += 1      # every out-of-block column shows its member's head: already final
+            assert np.array_equal(CM[blk], q)        # (the head of c is the largest value column c takes below the block)
+            assert np.array_equal(np.where(inb, pr, np.maximum(pr, CM[blk])), pr)
             return
         stats["slow"] += 1
         acc = pr.copy()
@@ -64,10 +65,27 @@ def scan_launch(tr, first, n, B, row, carry, stats):
             complete(x, lim, blk, True)
             exported[x] = True
         Q[blk + 1] = np.where(last[blk] >= 0, last[blk], Q[blk])
-    for j in range(n):                                      # C: k_cs_fix
-        x = first + j
-        if not exported[x]:
-            complete(x, first + (j // B) * B, j // B, True)
+    for blk in range(nb):                                   # C: k_cs_local<2>, the exact in-block walk
+        s = first + blk * B
+        # per-member cache (event, its row): the block-start heads with their final rows
+        tv = {m: (int(Q[blk, m]), row[Q[blk, m]].copy()) for m in range(M) if Q[blk, m] >= 0}
+        for h in range(s, min(s + B, first + n)):
+            pa, pb, c_ = p0[h], p1[h], cr[h]
+            v = np.full(M, -1, np.int64)
+            if pa >= 0:
+                def parent_row(p):
+                    hit = tv.get(int(cr[p]))
+                    if hit is not None and hit[0] == p:
+                        stats["cached"] += 1
+                        return hit[1]
+                    stats["table"] += 1
+                    # in-block: written earlier in this pass; out-of-block: finished by B or an earlier launch
+                    assert p < s and (p < first or exported[p]) or p >= s
+                    return row[p]
+                v = np.maximum(parent_row(pa), parent_row(pb))
+            v[c_] = h
+            row[h] = v
+            tv[int(c_)] = (h, v.copy())
     return Q[nb].copy()
 
 
@@ -82,7 +100,7 @@ def test_blocked_scan_equals_oracle(M, N, B, chunks, gen):
     ref = o.can_see()
     row = np.full((N, M), -1, np.int64)
     carry = np.full(M, -1, np.int64)
-    stats = {"final": 0, "fast": 0, "slow": 0}
+    stats = {"final": 0, "fast": 0, "slow": 0, "cached": 0, "table": 0}
     first = 0
     for n in chunks:
         carry = scan_launch(tr, first, n, B, row, carry, stats)
