@@ -43,6 +43,7 @@ struct sw_engine {
     int32_t *d_hist = nullptr, *d_cursor = nullptr, *d_order = nullptr, *d_gpos = nullptr, *d_lvl_start = nullptr;
     GDesc *d_gdesc = nullptr;
     long long *d_dbg = nullptr;
+    unsigned rb_epoch = 0;        // launches of k_rounds_batch (mask-cache key)
     int divide_impl = 5;          // 5 = round-batch on the whole GPU (default), 4 = level walker, 3 = per-event flags
     int n_sm = 0;
     int32_t *d_Wf = nullptr, *d_cev = nullptr, *d_rbmeta = nullptr, *d_rbtot = nullptr, *d_gchain = nullptr;   // round-batch state
@@ -268,6 +269,7 @@ int divide_round_batch(sw_engine *e, const DivParams &D) {
     const int grid = e->n_sm;
     R.L = std::max(1, std::min(RB_LMAX, grid * (RB_THREADS / 32) / e->M));
     R.maxmiss = RB_MAXMISS;
+    R.epoch = ++e->rb_epoch;
     if (const char *v = getenv("SW_RB_L")) R.L = std::max(1, std::min(R.L, atoi(v)));          // tuning knobs
     if (const char *v = getenv("SW_RB_MAXMISS")) R.maxmiss = std::max(0, atoi(v));
     R.row = e->d_row; R.p0 = e->d_p0; R.creator = e->d_creator; R.seq = e->d_seq; R.round = e->d_round;
@@ -276,6 +278,7 @@ int divide_round_batch(sw_engine *e, const DivParams &D) {
     R.ctot = e->d_rbtot; R.gchain = e->d_gchain;
     R.res = e->d_res; R.stake = e->d_stake; R.tot2 = D.tot2; R.scal = e->d_scal;
     R.wit = e->d_wit; R.W = e->d_W; R.SM = e->d_SM; R.dbg = e->d_dbg;
+    R.wlist = e->d_cev + e->cap; R.wcnt = e->d_rbmeta + 225;
     CK(cudaMemsetAsync(R.ccnt, 0, sizeof(int32_t) * 64, e->stream));
     CK(cudaMemsetAsync(R.cmin, 0x7f, sizeof(int32_t) * 64, e->stream));
     const int blocks = std::max(1, std::min(296, (D.n + 255) / 256));
@@ -353,7 +356,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(dalloc(&e->d_exported, cap)); CK(dalloc(&e->d_exp_list, cap + 8192)); CK(dalloc(&e->d_exp_m, cap + 8192)); CK(dalloc(&e->d_exp_cnt, cap / 2048 + 4));
         CK(dalloc(&e->d_cs_last, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_Q, (cap / 2048 + 5) * (size_t)M));
         CK(dalloc(&e->d_cs_CM, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_carry, (size_t)64));
-        CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, cap)); CK(dalloc(&e->d_rbmeta, (size_t)256));
+        CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, 2 * cap)); /* + the witness list of the current chunk */ CK(dalloc(&e->d_rbmeta, (size_t)256));
         CK(dalloc(&e->d_sc, cap)); CK(dalloc(&e->d_res, (size_t)2 * 64 * RB_LMAX));
         CK(dalloc(&e->d_rbtot, (size_t)64)); CK(dalloc(&e->d_gchain, (size_t)64 * RB_RING));
         CK(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -505,7 +508,7 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     StrongParams Q{};
     Q.M = e->M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
     Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
-    Q.coin = e->d_coin; Q.sig = e->d_sig;
+    Q.coin = e->d_coin; Q.sig = e->d_sig; Q.unit = e->unit ? 1 : 0;
     if (e->cansee_scan && first + n > e->n_rowed) {
         int rc = e->NC == 1 ? cansee_scan<1>(e) : cansee_scan<2>(e);
         if (rc < 0) return rc;
@@ -520,7 +523,12 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
         else rc = e->NC == 1 ? (e->unit ? launch_divide<1, true>(e, P) : launch_divide<1, false>(e, P))
                              : (e->unit ? launch_divide<2, true>(e, P) : launch_divide<2, false>(e, P));
         if (rc < 0) return rc;
-        const int wpb = 8, blocks = (n + wpb - 1) / wpb;
+        const int wpb = 8;
+        int blocks = (n + wpb - 1) / wpb;
+        if (e->divide_impl == 5) {                       // the round-batch path leaves the list of the chunk's witnesses
+            Q.list = e->d_cev + e->cap; Q.list_n = e->d_rbmeta + 225;
+            blocks = std::min(blocks, 4 * e->n_sm);
+        }
         if (e->NC == 1) k_strong<1><<<blocks, wpb * 32, 0, e->stream>>>(Q);
         else k_strong<2><<<blocks, wpb * 32, 0, e->stream>>>(Q);
         CK(cudaGetLastError());

@@ -58,6 +58,17 @@ __device__ __forceinline__ i64 wsum(u64 m, int unit, const i64 *stake_s) {
 // decide_fame's s(y) (swirld.py:245-254) for every witness y among [first, first+n):
 // hits[c_] = sum over members c whose latest seen event k = row(y)[c] has round EXACTLY
 // round(y)-1 (quirk Q15) of stake[c] * [c_ in SM(k)];  S[round y][creator y] = {c_ : 3 hits > 2 tot}.
+// 32x32 bit-matrix transpose across a warp: lane i gives row i, gets column i (bit b = row b's bit i)
+__device__ __forceinline__ unsigned rb_transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const unsigned m0 = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~m0) | ((y & ~m0) >> s)) : ((x & m0) | ((y & m0) << s));
+    }
+    return x;
+}
+
 struct StrongParams {
     int M, first, n, Rcap;
     const int32_t *creator, *row, *round;
@@ -68,48 +79,57 @@ struct StrongParams {
     const uint8_t *sig;  // [cap][64]
     const i64 *stake;
     i64 tot2;
+    int unit;
+    const int32_t *list, *list_n;   // optional: the witnesses of the range (else every event of the range is looked at)
 };
 
 template <int NC>
 __global__ void __launch_bounds__(256) k_strong(StrongParams P) {
     const int lane = threadIdx.x & 31;
-    const int h = P.first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
-    if (h >= P.first + P.n) return;
-    if (!P.wit[h]) return;
-    const int rh = P.round[h];
-    if (rh < 0 || rh >= P.Rcap) return;
-    if (lane == 0) P.coin[(size_t)rh * P.M + P.creator[h]] = P.sig[(size_t)h * 64] >> 7;
-    if (rh < 1) return;
-    const int M = P.M, r = rh - 1;
-    u64 mk[NC];
-    i64 st[NC], hits[NC];
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    const int cnt = P.list ? *P.list_n : P.n;
+    const int M = P.M;
+    for (int w = gw; w < cnt; w += nw) {
+        const int h = P.list ? P.list[w] : P.first + w;
+        if (!P.wit[h]) continue;
+        const int rh = P.round[h];
+        if (rh < 0 || rh >= P.Rcap) continue;
+        if (lane == 0) P.coin[(size_t)rh * M + P.creator[h]] = P.sig[(size_t)h * 64] >> 7;
+        if (rh < 1) continue;
+        const int r = rh - 1;
+        u64 mk[NC];
+        i64 st[NC], hits[NC];
 #pragma unroll
-    for (int j = 0; j < NC; j++) {
-        const int c = lane + 32 * j;
-        mk[j] = 0; st[j] = 0; hits[j] = 0;
-        if (c < M) {
-            const int k = P.row[(size_t)h * M + c];
-            if (k >= 0 && P.round[k] == r) mk[j] = P.SM[k];
-            st[j] = P.stake[c];
+        for (int j = 0; j < NC; j++) {
+            const int c = lane + 32 * j;
+            mk[j] = 0; st[j] = 0; hits[j] = 0;
+            if (c < M) {
+                const int k = P.row[(size_t)h * M + c];
+                if (k >= 0 && P.round[k] == r) mk[j] = P.SM[k];
+                st[j] = P.stake[c];
+            }
         }
+        __syncwarp();
+        // hits[c_] = stake of the members m whose latest seen event (of round r) sees witness c_ of round r:
+        // transpose the (member x column) bit matrix in 32x32 blocks, lane c_ then owns its column
+#pragma unroll
+        for (int jj = 0; jj < NC; jj++)
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const unsigned t = rb_transpose32((unsigned)(mk[jj] >> (32 * j)), lane);   // bit b: member jj*32+b
+                if (P.unit) hits[j] += __popc(t);
+                else
+                    for (int b = 0; b < 32; b++) {
+                        const i64 s = __shfl_sync(0xffffffffu, st[jj], b);
+                        hits[j] += ((t >> b) & 1) ? s : 0;
+                    }
+            }
+        u64 smask = 0;
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+            smask |= (u64)__ballot_sync(0xffffffffu, 3 * hits[j] > P.tot2) << (32 * j);
+        if (lane == 0) P.S[(size_t)rh * M + P.creator[h]] = smask;
     }
-#pragma unroll
-    for (int jj = 0; jj < NC; jj++) {
-        for (int l = 0; l < 32; l++) {
-            if (jj * 32 + l >= M) break;
-            const u64 m = __shfl_sync(0xffffffffu, mk[jj], l);
-            if (m == 0) continue;
-            const i64 s = __shfl_sync(0xffffffffu, st[jj], l);
-#pragma unroll
-            for (int j = 0; j < NC; j++)
-                if ((m >> (lane + 32 * j)) & 1) hits[j] += s;
-        }
-    }
-    u64 smask = 0;
-#pragma unroll
-    for (int j = 0; j < NC; j++)
-        smask |= (u64)__ballot_sync(0xffffffffu, 3 * hits[j] > P.tot2) << (32 * j);
-    if (lane == 0) P.S[(size_t)rh * M + P.creator[h]] = smask;
 }
 
 // ---------------------------------------------------------------- K3: decide_fame

@@ -38,10 +38,12 @@ namespace cg = cooperative_groups;
 #define RB_LMAX 64          // pending events tested per chain and step (at most)
 #define RB_THREADS 512       // 16 warps per CTA, one CTA per SM
 #define RB_RING 256          // per-member ring of recent events (what precedes the chunk)
+#define RB_NPOLL 24          // polls of a mask that is being produced before the reader computes it itself
 #define RB_MAXMISS 0         // an event with more unprepared S_r masks than this waits for a later step
 
 struct RbParams {
     int M, first, n, Rcap, L, maxmiss;
+    unsigned epoch;             // launch counter (part of the mask-cache key)
     const int32_t *row, *p0, *creator, *seq;
     int32_t *round;             // [cap] out
     int32_t *Wf;                // [Rcap][M] first event of round >= r per member
@@ -60,16 +62,27 @@ struct RbParams {
     uint8_t *wit;               // [cap]   (finish kernels)
     int32_t *W;                 // [Rcap][M] the reference's witnesses table
     u64 *SM;                    // [cap]
+    int32_t *wlist, *wcnt;      // witnesses of the chunk (k_rb_witness -> k_strong)
 };
 
 // ---- per-member event lists of the chunk
-__global__ void k_rb_count(RbParams P) {
+__global__ void __launch_bounds__(256) k_rb_count(RbParams P) {
+    __shared__ int cnt[64], mn[64], mx[64];                   // per CTA first, then one global atomic per member
+    if (threadIdx.x < 64) { cnt[threadIdx.x] = 0; mn[threadIdx.x] = 0x7fffffff; mx[threadIdx.x] = 0; }
+    __syncthreads();
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.n; j += gridDim.x * blockDim.x) {
         const int h = P.first + j, c = P.creator[h];
         const int sq = P.seq[h];
-        atomicAdd(&P.ccnt[c], 1);
-        atomicMin(&P.cmin[c], sq);
-        atomicMax(&P.ctot[c], sq + 1);
+        atomicAdd(&cnt[c], 1);
+        atomicMin(&mn[c], sq);
+        atomicMax(&mx[c], sq + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < P.M && cnt[threadIdx.x] > 0) {
+        const int c = threadIdx.x;
+        atomicAdd(&P.ccnt[c], cnt[c]);
+        atomicMin(&P.cmin[c], mn[c]);
+        atomicMax(&P.ctot[c], mx[c]);
     }
 }
 __global__ void k_rb_offsets(RbParams P) {       // one warp
@@ -85,7 +98,7 @@ __global__ void k_rb_offsets(RbParams P) {       // one warp
     P.coff[lane] = sa - a;
     P.coff[lane + 32] = tot_a + sb - b;
     if (lane == 31) P.coff[64] = tot_a + sb;
-    if (lane == 0) *P.bar = 0;
+    if (lane == 0) { *P.bar = 0; *P.wcnt = 0; }
 }
 __global__ void k_rb_scatter(RbParams P) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < P.n; j += gridDim.x * blockDim.x) {
@@ -100,17 +113,6 @@ __global__ void k_rb_tail(RbParams P) {
         const int h = P.first + j, c = P.creator[h], sq = P.seq[h];
         if (P.ctot[c] - sq <= RB_RING) P.gchain[c * RB_RING + (sq & (RB_RING - 1))] = h;
     }
-}
-
-// 32x32 bit-matrix transpose across a warp: lane i gives row i, gets column i (bit b = row b's bit i)
-__device__ __forceinline__ unsigned rb_transpose32(unsigned x, int lane) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        const unsigned m0 = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
-        const unsigned y = __shfl_xor_sync(0xffffffffu, x, s);
-        x = (lane & s) ? ((x & ~m0) | ((y & ~m0) >> s)) : ((x & m0) | ((y & m0) << s));
-    }
-    return x;
 }
 
 // Grid-wide barrier for the co-resident (cooperatively launched) grid.  *ctr is zero at launch and
@@ -130,7 +132,11 @@ __device__ __forceinline__ void rb_grid_barrier(unsigned *ctr, unsigned &target)
     __syncthreads();
 }
 
-__device__ __forceinline__ u64 rb_key(int r) { return (u64)(r + 1) * 0x9E3779B97F4A7C15ull; }
+// validity key of a cached mask: the round it was computed for and the launch that computed it (Wf_r can
+// gain members between two launches, so a mask of an earlier launch is never reused)
+__device__ __forceinline__ u64 rb_key(int r, unsigned epoch) {
+    return (u64)(r + 1) * 0x9E3779B97F4A7C15ull ^ (u64)(epoch + 1) * 0xC2B2AE3D27D4EB4Full;
+}
 
 template <int NC, bool UNIT>
 __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
@@ -145,8 +151,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
     const i64 thr = P.tot2 / 3;
     const bool lead = blockIdx.x == 0;
     // per-step results, double buffered: first hit of a chain as (position << 32 | event), first deferred position
-    u64 *hitmin = reinterpret_cast<u64 *>(P.res);             // [2][64]
-    int *unkmin = reinterpret_cast<int *>(P.res + 2 * 64 * sizeof(u64));   // [2][64]
+    // (three buffers: the tests of step s+1 start without a grid barrier after the bookkeeping of step s)
+    u64 *hitmin = reinterpret_cast<u64 *>(P.res);             // [3][64]
+    int *unkmin = reinterpret_cast<int *>(P.res + 3 * 64 * sizeof(u64));   // [3][64]
 
     int rtop = max(P.scal[SC_MAX_ROUND], 0);
     for (int i = tid; i < RB_WR * 64; i += blockDim.x) {
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         off[c] = o; len[c] = l; pos[c] = 0; cur[c] = cu;
         cmin_s[c] = c < M ? P.cmin[c] : 0; ctot_s[c] = c < M ? P.ctot[c] : 0;
     }
-    if (lead && tid < 128) { hitmin[tid] = ~0ull; unkmin[tid] = 0x7fffffff; }
+    if (lead && tid < 192) { hitmin[tid] = ~0ull; unkmin[tid] = 0x7fffffff; }
     __syncthreads();
     if (tid < M && len[tid] > 0 && cur[tid] == 0) {          // a member's root opens round 0 for it
         const int h0 = P.cev[off[tid]];
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
 
     long long c_miss = 0, tG0 = 0, tG1 = 0, c_g = 0, c_gmax = 0;
     // ---- P_r(h) by one warp; pre = can_see row of h with the own column set back to the self-parent
-    auto eval = [&](const int (&pre)[NC], int r, bool may_defer) -> int {
+    auto eval = [&](const int (&pre)[NC], const int (&hi_ev)[NC], int r, bool may_defer) -> int {
         int W[NC];
         bool live[NC];
         u64 m[NC];
@@ -212,16 +219,25 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         }
         tG0 = clock64(); tG1 = tG0;
         if (lv <= thr) return 0;                              // hits[c_] <= stake of the live members
-        const u64 key = rb_key(r);
-        bool valid[NC];
+        const u64 key = rb_key(r, P.epoch);
+        // The masks are produced by other warps in this same step, without a barrier in between: an entry
+        // that the producers will write (its event lies inside the member's prepared range) is polled
+        // until its key shows up; anything else counts as a miss right away.
+        bool valid[NC], expect[NC];
 #pragma unroll
-        for (int j = 0; j < NC; j++) {
-            valid[j] = true;
-            if (live[j]) {
-                const ulonglong2 e = __ldcg(P.sc + pre[j]);
-                valid[j] = (e.x ^ e.y) == key;
-                m[j] = e.x;
-            }
+        for (int j = 0; j < NC; j++) { valid[j] = !live[j]; expect[j] = live[j] && pre[j] <= hi_ev[j]; }
+        for (int poll = 0; poll < RB_NPOLL; poll++) {
+#pragma unroll
+            for (int j = 0; j < NC; j++)
+                if (!valid[j]) {
+                    const ulonglong2 e = __ldcg(P.sc + pre[j]);
+                    valid[j] = (e.x ^ e.y) == key;
+                    m[j] = e.x;
+                }
+            bool wait = false;
+#pragma unroll
+            for (int j = 0; j < NC; j++) wait |= expect[j] && !valid[j];
+            if (!__any_sync(0xffffffffu, wait)) break;
         }
         __syncwarp();
         {   // an event far ahead of the tested windows sees events nobody prepared: leave it for a later step
@@ -303,25 +319,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
         if (rmin == 0x7fffffff) break;                        // every chain is done
-        const int buf = step & 1;
+        const int buf = step % 3;
         // ---- this warp's test of the step: fetch its inputs now, they are needed after the barrier
         const int tc = gw / L, tj = gw - tc * L;              // M * L <= nw: one (chain, position) per warp
-        bool act = false;
+        const bool act = tc < M && pos[tc] < len[tc] && cur[tc] == rmin && pos[tc] + tj < len[tc];
         int th = -1, tpa = -1, tpre[NC];
-        if (tc < M && pos[tc] < len[tc] && cur[tc] == rmin && pos[tc] + tj < len[tc]) {
-            act = true;
-            th = P.cev[off[tc] + pos[tc] + tj];
-            tpa = P.p0[th];
-#pragma unroll
-            for (int j = 0; j < NC; j++) {
-                const int c = lane + 32 * j;
-                tpre[j] = c < M ? __ldcg(P.row + (size_t)th * M + c) : -1;
-            }
-        }
+        if (act) th = P.cev[off[tc] + pos[tc] + tj];          // (its dependent loads are issued after the range arithmetic)
         // ---- S_rmin(k) of every event the tests can meet: per member, its events from Wf_rmin[c] up to
         //      the end of its pending window (one warp per event, all SMs).  Ranges in registers:
         //      lane holds members lane and lane+32.
-        int rlo[2], rcnt[2], rinc[2];
+        int rlo[2], rcnt[2], rinc[2], rhi[2];
         const bool mir = in_mirror(rmin);
 #pragma unroll
         for (int j = 0; j < 2; j++) {
@@ -336,6 +343,17 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
                 }
             }
             rlo[j] = lo; rcnt[j] = cnt;
+            // the last event of the prepared range, as an event index (what a test compares its pre[] with)
+            int hv = -1;
+            if (cnt > 0) {
+                const int sq = lo + cnt - 1;
+                if (len[c] > 0 && sq >= cmin_s[c]) hv = P.cev[off[c] + sq - cmin_s[c]];
+                else {
+                    const int before = len[c] > 0 ? cmin_s[c] : ctot_s[c];
+                    hv = (before - sq <= RB_RING) ? __ldcg(P.gchain + c * RB_RING + (sq & (RB_RING - 1))) : -1;
+                }
+            }
+            rhi[j] = hv;
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
@@ -344,11 +362,20 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         const int totA = __shfl_sync(0xffffffffu, rinc[0], 31);
         rinc[1] += totA;
         const int total = __shfl_sync(0xffffffffu, rinc[1], 31);
+        if (act) {
+            tpa = P.p0[th];
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const int c = lane + 32 * j;
+                tpre[j] = c < M ? __ldcg(P.row + (size_t)th * M + c) : -1;
+            }
+        }
         const long long tA0 = clock64();
         {
-            const u64 key = rb_key(rmin);
-            for (int i = gw; i < total; i += nw) {
-                // member whose range holds candidate i: the first with inclusive prefix > i
+            const u64 key = rb_key(rmin, P.epoch);
+            // candidate i -> its event (the member whose range holds i is the first with inclusive prefix > i)
+            auto candidate = [&](int i) -> int {
+                if (i >= total) return -1;
                 int c, base, lo;
                 if (i < totA) {
                     c = __popc(__ballot_sync(0xffffffffu, rinc[0] <= i));
@@ -359,34 +386,43 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
                     base = __shfl_sync(0xffffffffu, rinc[1] - rcnt[1], l); lo = __shfl_sync(0xffffffffu, rlo[1], l);
                 }
                 const int sq = lo + (i - base);
-                int k;
-                if (len[c] > 0 && sq >= cmin_s[c]) k = P.cev[off[c] + sq - cmin_s[c]];
-                else {      // before the chunk: the ring holds the member's last RB_RING events of the earlier chunks
-                    const int before = len[c] > 0 ? cmin_s[c] : ctot_s[c];
-                    k = (before - sq <= RB_RING) ? __ldcg(P.gchain + c * RB_RING + (sq & (RB_RING - 1))) : -1;
-                }
-                if (k < 0) continue;
-                u64 mask = 0;
+                if (len[c] > 0 && sq >= cmin_s[c]) return P.cev[off[c] + sq - cmin_s[c]];
+                // before the chunk: the ring holds the member's last RB_RING events of the earlier chunks
+                const int before = len[c] > 0 ? cmin_s[c] : ctot_s[c];
+                return (before - sq <= RB_RING) ? __ldcg(P.gchain + c * RB_RING + (sq & (RB_RING - 1))) : -1;
+            };
+            for (int i = gw; i < total; i += 2 * nw) {       // two rows in flight per trip
+                const int k0 = candidate(i), k1 = candidate(i + nw);
+                int v0[NC], v1[NC], wv[NC];
 #pragma unroll
                 for (int j = 0; j < NC; j++) {
                     const int cc = lane + 32 * j;
-                    const int wv = cc < M ? wrow(rmin, cc) : -1;
-                    const int v = cc < M ? __ldcg(P.row + (size_t)k * M + cc) : -1;
-                    mask |= (u64)__ballot_sync(0xffffffffu, wv >= 0 && v >= wv) << (32 * j);
+                    wv[j] = cc < M ? wrow(rmin, cc) : -1;
+                    v0[j] = (k0 >= 0 && cc < M) ? __ldcg(P.row + (size_t)k0 * M + cc) : -1;
+                    v1[j] = (k1 >= 0 && cc < M) ? __ldcg(P.row + (size_t)k1 * M + cc) : -1;
                 }
-                if (lane == 0) P.sc[k] = make_ulonglong2(mask, mask ^ key);
+                u64 mask0 = 0, mask1 = 0;
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    mask0 |= (u64)__ballot_sync(0xffffffffu, wv[j] >= 0 && v0[j] >= wv[j]) << (32 * j);
+                    mask1 |= (u64)__ballot_sync(0xffffffffu, wv[j] >= 0 && v1[j] >= wv[j]) << (32 * j);
+                }
+                if (lane == 0 && k0 >= 0) P.sc[k0] = make_ulonglong2(mask0, mask0 ^ key);
+                if (lane == 0 && k1 >= 0) P.sc[k1] = make_ulonglong2(mask1, mask1 ^ key);
             }
         }
         const long long tA1 = clock64();
-        rb_grid_barrier(P.bar, bar_target);
-        const long long tS1 = clock64();
+        const long long tS1 = tA1;
         // ---- test the pending windows
         if (act) {
             int hit = 0;
             if (tpa >= 0) {
 #pragma unroll
                 for (int j = 0; j < NC; j++) if (lane + 32 * j == tc) tpre[j] = tpa;
-                hit = eval(tpre, rmin, tj > 0);
+                int thi[NC];
+#pragma unroll
+                for (int j = 0; j < NC; j++) thi[j] = rhi[j];
+                hit = eval(tpre, thi, rmin, tj > 0);
             }
             if (lane == 0) {
                 if (hit == 1) atomicMin(hitmin + buf * 64 + tc, ((u64)tj << 32) | (unsigned)th);
@@ -434,7 +470,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
                 pos[c] += nfinal;
             }
             s_nfin[tid] = nfinal; s_base[tid] = o;
-            if (lead) { hitmin[(buf ^ 1) * 64 + tid] = ~0ull; unkmin[(buf ^ 1) * 64 + tid] = 0x7fffffff; }
+            if (lead) { const int nb2 = (buf + 2) % 3; hitmin[nb2 * 64 + tid] = ~0ull; unkmin[nb2 * 64 + tid] = 0x7fffffff; }
         }
         __syncthreads();
         // final rounds of the events before the first hit, spread over the CTAs
@@ -469,7 +505,10 @@ __global__ void k_rb_witness(RbParams P) {
         const int h = P.first + j, pa = P.p0[h], r = P.round[h];
         const bool wit = pa < 0 || r > P.round[pa];
         P.wit[h] = wit ? 1 : 0;
-        if (wit && r >= 0 && r < P.Rcap) P.W[(size_t)r * P.M + P.creator[h]] = h;
+        if (wit && r >= 0 && r < P.Rcap) {
+            P.W[(size_t)r * P.M + P.creator[h]] = h;
+            P.wlist[atomicAdd(P.wcnt, 1)] = h;                // k_strong runs over the witnesses only
+        }
     }
 }
 // ---- SM(h) = {c_ : W[round h][c_] >= 0 and row(h)[c_] >= W[round h][c_]}, one warp per event
