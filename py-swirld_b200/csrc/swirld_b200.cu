@@ -52,7 +52,7 @@ struct sw_engine {
     int cansee_scan = 0;          // 1 = can_see by the blocked scan k_cs_* (SW_CANSEE_IMPL=scan), 0 = fused into the walker
     int n_rowed = 0;              // events whose can_see row is complete (cansee_scan)
     uint8_t *d_exported = nullptr;
-    int32_t *d_exp_list = nullptr, *d_exp_m = nullptr, *d_exp_cnt = nullptr, *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_CM = nullptr, *d_cs_carry = nullptr;
+    int32_t *d_exp_list = nullptr, *d_exp_m = nullptr, *d_exp_cnt = nullptr, *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_carry = nullptr;
     double *d_t = nullptr;
     uint8_t *d_sig = nullptr;
     int32_t *d_row = nullptr, *d_round = nullptr;
@@ -61,7 +61,7 @@ struct sw_engine {
     int8_t *d_famous_ev = nullptr;
     // per round
     int32_t *d_W = nullptr, *d_rem = nullptr, *d_newc = nullptr;
-    u64 *d_S = nullptr, *d_V = nullptr;
+    u64 *d_S = nullptr;
     int8_t *d_famous = nullptr;
     uint8_t *d_consensus = nullptr, *d_done = nullptr, *d_coin = nullptr;
     i64 *d_stake = nullptr;
@@ -213,7 +213,9 @@ int cansee_scan(sw_engine *e) {
     if (n <= 0) return 0;
     CsParams C{};
     C.M = e->M; C.first = first; C.n = n;
-    C.B = std::min(n, n >= 200000 ? 4096 : 2048);
+    // block length: the in-block walks are serial in B, the boundary pass in n/B (SW_CS_B overrides)
+    C.B = std::min(n, n >= 200000 ? 4096 : 1024);
+    if (const char *v = getenv("SW_CS_B")) C.B = std::max(64, std::min(n, atoi(v)));
     C.nb = (n + C.B - 1) / C.B;
     C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.row = e->d_row;
     C.exported = e->d_exported; C.exp_list = e->d_exp_list; C.exp_m = e->d_exp_m; C.exp_cnt = e->d_exp_cnt;
@@ -353,17 +355,18 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64)); CK(dalloc(&e->d_height, cap));
         CK(dalloc(&e->d_hist, cap + 2)); CK(dalloc(&e->d_cursor, cap + 2)); CK(dalloc(&e->d_order, cap));
         CK(dalloc(&e->d_gpos, cap)); CK(dalloc(&e->d_lvl_start, cap + 2)); CK(dalloc(&e->d_gdesc, cap));
-        CK(dalloc(&e->d_exported, cap)); CK(dalloc(&e->d_exp_list, cap + 8192)); CK(dalloc(&e->d_exp_m, cap + 8192)); CK(dalloc(&e->d_exp_cnt, cap / 2048 + 4));
-        CK(dalloc(&e->d_cs_last, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_Q, (cap / 2048 + 5) * (size_t)M));
-        CK(dalloc(&e->d_cs_CM, (cap / 2048 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_carry, (size_t)64));
+        CK(dalloc(&e->d_exported, cap)); CK(dalloc(&e->d_exp_list, cap + 8192)); CK(dalloc(&e->d_exp_m, cap + 8192)); CK(dalloc(&e->d_exp_cnt, cap / 64 + 4));
+        CK(dalloc(&e->d_cs_last, (cap / 64 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_Q, (cap / 64 + 5) * (size_t)M));
+        CK(dalloc(&e->d_cs_carry, (size_t)64));
         CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, 2 * cap)); /* + the witness list of the current chunk */ CK(dalloc(&e->d_rbmeta, (size_t)256));
         CK(dalloc(&e->d_sc, cap)); CK(dalloc(&e->d_res, (size_t)2 * 64 * RB_LMAX));
         CK(dalloc(&e->d_rbtot, (size_t)64)); CK(dalloc(&e->d_gchain, (size_t)64 * RB_RING));
         CK(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
         CK(dalloc(&e->d_dbg, (size_t)40)); CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 40, e->stream));
-        CK(dalloc(&e->d_row, cap * M)); CK(dalloc(&e->d_T, cap * M)); CK(dalloc(&e->d_SM, cap));
+        CK(dalloc(&e->d_row, cap * M)); CK(dalloc(&e->d_SM, cap));
+        if (e->divide_impl != 5) CK(dalloc(&e->d_T, cap * M));           // strongly-sees matrices: level walker only
         CK(dalloc(&e->d_round, cap)); CK(dalloc(&e->d_wit, cap)); CK(dalloc(&e->d_famous_ev, cap));
-        CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_S, RM)); CK(dalloc(&e->d_V, RM)); CK(dalloc(&e->d_famous, RM));
+        CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_S, RM)); CK(dalloc(&e->d_famous, RM));
         CK(dalloc(&e->d_consensus, (size_t)e->Rcap)); CK(dalloc(&e->d_done, (size_t)e->Rcap)); CK(dalloc(&e->d_coin, RM));
         CK(dalloc(&e->d_rem, (size_t)e->Rcap)); CK(dalloc(&e->d_newc, (size_t)e->Rcap));
         CK(dalloc(&e->d_stake, (size_t)M)); CK(dalloc(&e->d_scal, (size_t)SC_COUNT));
@@ -388,9 +391,9 @@ void sw_destroy(sw_engine *e) {
     fold_spans(e);
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
-    void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_CM, e->d_cs_carry, e->d_exported, e->d_exp_list, e->d_exp_m, e->d_exp_cnt, e->d_coin, e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
+    void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_carry, e->d_exported, e->d_exp_list, e->d_exp_m, e->d_exp_cnt, e->d_coin, e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
                     e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
-                    e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_V, e->d_famous, e->d_consensus,
+                    e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
                     e->d_batch_ev, e->d_batch_seg, e->d_perm, e->d_ts, e->d_key, e->d_seg_start, e->d_seg_fw,
                     e->d_seg_nf, e->d_seg_white, e->d_rounds_in, e->d_flush};

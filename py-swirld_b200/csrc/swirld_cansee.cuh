@@ -216,67 +216,93 @@ __device__ __forceinline__ void cs_complete_row(const CsParams &P, int x, int li
 // ---- B: block by block, the rows later blocks depend on.  One CTA; per block: finish the listed rows
 // (one warp per row, the partial rows of a warp's batch are fetched together), then install the block's
 // last events as the new heads.  The next block's list is fetched while this one is processed.
-#define CS_LIST 768
+#define CS_LIST 512
 template <int NC>
 __global__ void __launch_bounds__(1024, 1) k_cs_boundary(CsParams P) {
     constexpr int MS = NC * 32;
     __shared__ int32_t Q[MS], newq[MS];
     __shared__ int32_t S[MS][MS], Snew[MS][MS];
-    __shared__ int32_t lst[2][CS_LIST], lstm[2][CS_LIST];
-    __shared__ int cnt_s[2];
+    __shared__ int32_t lst[3][CS_LIST], lstm[3][CS_LIST];       // lists of blocks blk, blk+1, blk+2
+    __shared__ int cnt_s[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = P.M;
     if (tid < MS) { Q[tid] = tid < M ? P.carry[tid] : -1; newq[tid] = -1; }
-    if (tid == 0) cnt_s[0] = P.exp_cnt[0];
+    if (tid < 2) cnt_s[tid] = tid < P.nb ? P.exp_cnt[tid] : 0;
     __syncthreads();
     for (int i = tid; i < MS * MS; i += 1024) {
         const int m = i / MS, c = i % MS;
         S[m][c] = (m < M && c < M && Q[m] >= 0) ? P.row[(size_t)Q[m] * M + c] : -1;
     }
-    if (tid < min(cnt_s[0], CS_LIST)) { lst[0][tid] = P.exp_list[P.first + tid]; lstm[0][tid] = P.exp_m[P.first + tid]; }
-    __syncthreads();
-    for (int blk = 0; blk < P.nb; blk++) {
-        const int buf = blk & 1, lim = P.first + blk * P.B, cnt = cnt_s[buf];
-        const int32_t *glist = P.exp_list + lim, *glm = P.exp_m + lim;
-        if (tid < M) P.Qtab[(size_t)blk * M + tid] = Q[tid];             // heads for pass 2
-        // the next block's list: loads now, shared-memory stores after this block's rows
-        int ncnt = 0, nx = -1, nm = -1;
-        if (blk + 1 < P.nb) {
-            ncnt = P.exp_cnt[blk + 1];
-            if (tid < min(ncnt, CS_LIST)) { nx = P.exp_list[lim + P.B + tid]; nm = P.exp_m[lim + P.B + tid]; }
+    for (int b = 0; b < 2 && b < P.nb; b++)
+        if (tid < min(cnt_s[b], CS_LIST)) {
+            lst[b][tid] = P.exp_list[P.first + b * P.B + tid]; lstm[b][tid] = P.exp_m[P.first + b * P.B + tid];
         }
-        for (int i0 = warp; i0 < cnt; i0 += 128) {                      // up to four rows per warp and trip
-            int x[4], mm[4], pr[4][NC];
+    __syncthreads();
+    // a warp's first four rows of a block (entries warp, warp+32, ...) are fetched one block ahead
+    int xc[4], mc[4], prc[4][NC];
+    auto fetch = [&](int blk, int b, int (&x)[4], int (&mm)[4], int (&pr)[4][NC]) {
+        const int cnt = blk < P.nb ? cnt_s[b] : 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = i0 + 32 * u;
-                x[u] = -1; mm[u] = -1;
-                if (i < cnt) { x[u] = i < CS_LIST ? lst[buf][i] : glist[i]; mm[u] = i < CS_LIST ? lstm[buf][i] : glm[i]; }
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const int c = lane + 32 * j;
-                    pr[u][j] = (x[u] >= 0 && c < M) ? P.row[(size_t)x[u] * M + c] : 0;
-                }
+        for (int u = 0; u < 4; u++) {
+            const int i = warp + 32 * u;
+            x[u] = -1; mm[u] = -1;
+            if (i < cnt) {
+                x[u] = i < CS_LIST ? lst[b][i] : P.exp_list[P.first + blk * P.B + i];
+                mm[u] = i < CS_LIST ? lstm[b][i] : P.exp_m[P.first + blk * P.B + i];
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (x[u] < 0) continue;                                  // uniform
-                cs_complete_row<NC>(P, x[u], lim, lane, Q, S, pr[u]);
-                if (mm[u] >= 0) {                                        // the member's head after this block
-#pragma unroll
-                    for (int j = 0; j < NC; j++) if (lane + 32 * j < M) Snew[mm[u]][lane + 32 * j] = pr[u][j];
-                    if (lane == 0) newq[mm[u]] = x[u];
-                }
+            for (int j = 0; j < NC; j++) {
+                const int c = lane + 32 * j;
+                pr[u][j] = (x[u] >= 0 && c < M) ? P.row[(size_t)x[u] * M + c] : 0;
             }
+        }
+    };
+    fetch(0, 0, xc, mc, prc);
+    for (int blk = 0; blk < P.nb; blk++) {
+        const int b0 = blk % 3, b1 = (blk + 1) % 3, b2 = (blk + 2) % 3;
+        const int lim = P.first + blk * P.B, cnt = cnt_s[b0];
+        if (tid < M) P.Qtab[(size_t)blk * M + tid] = Q[tid];             // heads for pass 2
+        // loads for later blocks first: the list of blk+2, the first rows of blk+1 (partial rows of
+        // pass 1: nothing in this loop writes them before their own turn)
+        int ncnt = 0, nx = -1, nm = -1;
+        if (blk + 2 < P.nb) {
+            ncnt = P.exp_cnt[blk + 2];
+            if (tid < min(ncnt, CS_LIST)) { nx = P.exp_list[lim + 2 * P.B + tid]; nm = P.exp_m[lim + 2 * P.B + tid]; }
+        }
+        int xn[4], mn[4], prn[4][NC];
+        fetch(blk + 1, b1, xn, mn, prn);
+        auto finish = [&](int x, int mm, int (&pr)[NC]) {
+            cs_complete_row<NC>(P, x, lim, lane, Q, S, pr);
+            if (mm >= 0) {                                               // the member's head after this block
+#pragma unroll
+                for (int j = 0; j < NC; j++) if (lane + 32 * j < M) Snew[mm][lane + 32 * j] = pr[j];
+                if (lane == 0) newq[mm] = x;
+            }
+        };
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (xc[u] >= 0) finish(xc[u], mc[u], prc[u]);   // (uniform per warp)
+        for (int i = warp + 128; i < cnt; i += 32) {                     // long lists: the rest on demand
+            const int x = i < CS_LIST ? lst[b0][i] : P.exp_list[lim + i];
+            const int mm = i < CS_LIST ? lstm[b0][i] : P.exp_m[lim + i];
+            int pr[NC];
+#pragma unroll
+            for (int j = 0; j < NC; j++) pr[j] = lane + 32 * j < M ? P.row[(size_t)x * M + lane + 32 * j] : 0;
+            finish(x, mm, pr);
         }
         __syncthreads();
         for (int i = tid; i < MS * MS; i += 1024) {
             const int m = i / MS, c = i % MS;
             if (newq[m] >= 0) S[m][c] = Snew[m][c];
         }
-        if (tid < min(ncnt, CS_LIST)) { lst[buf ^ 1][tid] = nx; lstm[buf ^ 1][tid] = nm; }
-        if (tid == 0) cnt_s[buf ^ 1] = ncnt;
+        if (tid < min(ncnt, CS_LIST)) { lst[b2][tid] = nx; lstm[b2][tid] = nm; }
+        if (tid == 0) cnt_s[b2] = ncnt;
         __syncthreads();
         if (tid < MS && newq[tid] >= 0) { Q[tid] = newq[tid]; newq[tid] = -1; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            xc[u] = xn[u]; mc[u] = mn[u];
+#pragma unroll
+            for (int j = 0; j < NC; j++) prc[u][j] = prn[u][j];
+        }
         __syncthreads();
     }
     if (tid < M) { P.carry[tid] = Q[tid]; P.Qtab[(size_t)P.nb * M + tid] = Q[tid]; }

@@ -432,6 +432,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
             c_maxev = e1 > c_maxev ? e1 : c_maxev; c_sumev += e1; c_nev++; c_def += hit == 2;
             c_g += tG1 - tG0; c_gmax = max(c_gmax, tG1 - tG0);
         }
+        // the rows the next steps will read first (masks and tests of the events just beyond the windows):
+        // pull them into L2 now, off the critical path
+        if (tc < M && lane < NC * 2) {
+            const int idx = pos[tc] + L + tj;
+            if (idx < len[tc]) {
+                const int h = P.cev[off[tc] + idx];
+                const char *ptr = reinterpret_cast<const char *>(P.row + (size_t)h * M) + lane * 128;
+                if (lane * 128 < M * 4) asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr));
+            }
+        }
         const long long t1 = clock64();
         rb_grid_barrier(P.bar, bar_target);
         const long long t2 = clock64();

@@ -183,3 +183,27 @@ def test_engine_edge_cases():
     assert ei.value.code in (-5, -7, -6)
     with pytest.raises(engine.EngineError):          # M above this build's limit
         engine.Engine(65, 16)
+
+
+@pytest.mark.parametrize("M,N,K,gen", [(16, 100000, 4096, "gossip"), (64, 262144, 65536, "gossip"),
+                                       (64, 40000, 8192, "adversarial")])
+def test_append_everything_first(M, N, K, gen):
+    """The bench's resident pattern: every event appended before the first divide_rounds, so can_see is
+    scanned for the whole trace at once (hundreds of blocks; 4096-event blocks from 200 000 events on),
+    then the same engine is rewound and run again (sw_rewind keeps the columns, clears the consensus)."""
+    from swirld_b200 import engine, traces
+    from swirld_b200.traces import chunks
+    tr = getattr(traces, gen)(M, N, 5)
+    o = orc.run_oracle(tr, K)
+    e = engine.Engine(M, N)
+    e.append_trace(tr)
+    for rep in range(2):
+        if rep:
+            e.rewind()
+        for first, cnt in chunks(N, K):
+            e.divide_rounds(first, cnt)
+            e.decide_fame()
+        assert np.array_equal(o["round"], e.rounds()), "rounds differ (pass %d)" % rep
+        assert np.array_equal(o["oracle"].can_see(), e.can_see()), "can_see differs (pass %d)" % rep
+        r = e.results()
+        assert np.array_equal(o["famous"], r["famous"]) and np.array_equal(o["witness"], r["witness"])
