@@ -536,7 +536,7 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
         else k_strong<2><<<blocks, wpb * 32, 0, e->stream>>>(Q);
         CK(cudaGetLastError());
     }
-    e->stats.kernel_launches += 2;
+    e->stats.kernel_launches += e->divide_impl == 5 ? 1 : 2;      // k_strong (+ the walker; the round-batch kernels count themselves)
     e->stats.events_divided += n;
     e->n_divided += n;
     return SW_OK;
