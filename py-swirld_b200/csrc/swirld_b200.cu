@@ -36,7 +36,8 @@ struct sw_engine {
     std::vector<int32_t> h_creator, h_head, h_count;
     int32_t *h_height = nullptr, *h_seq = nullptr;   // pinned, cap entries: sources of asynchronous copies
     cudaStream_t copy_stream = nullptr;              // sw_append's copies run beside the kernels of earlier chunks
-    cudaEvent_t ev_append = nullptr;
+    struct PendingAppend { int base; cudaEvent_t done; };
+    std::vector<PendingAppend> appends;              // copies (+ eager can_see scans) the compute stream has not waited for yet
     int n_events = 0, n_divided = 0, n_tx = 0;
     // device columns
     int32_t *d_p0 = nullptr, *d_p1 = nullptr, *d_creator = nullptr, *d_seq = nullptr, *d_height = nullptr;
@@ -123,7 +124,9 @@ struct Span {
 };
 
 void fold_spans(sw_engine *e) {
+    std::vector<TimedSpan> pending;
     for (auto &s : e->spans) {
+        if (cudaEventQuery(s.b) == cudaErrorNotReady) { pending.push_back(s); continue; }   // (a scan still running on the copy stream)
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
             if (s.cat == 0) e->stats.ms_divide_rounds += ms;
@@ -134,7 +137,19 @@ void fold_spans(sw_engine *e) {
         }
         e->pool.push_back(s.a); e->pool.push_back(s.b);
     }
-    e->spans.clear();
+    e->spans.swap(pending);
+}
+
+// Make the compute stream wait for the appended batches that start below `upto` (all of them: upto < 0).
+int wait_appends(sw_engine *e, int upto) {
+    size_t k = 0;
+    for (auto &a : e->appends) {
+        if (upto >= 0 && a.base >= upto) { e->appends[k++] = a; continue; }
+        CK(cudaStreamWaitEvent(e->stream, a.done, 0));
+        e->pool.push_back(a.done);           // (re-recorded only after later work was enqueued behind the wait)
+    }
+    e->appends.resize(k);
+    return 0;
 }
 
 int device_error(sw_engine *e) {     // after a sync: did a kernel flag an error?
@@ -207,9 +222,11 @@ int launch_levels(sw_engine *e, const Div4Params &Q) {
 }
 
 // can_see rows of every appended event that does not have one yet: blocked scan (k_cs_*)
+// `st`: the compute stream (lazily, from sw_divide_rounds) or the copy stream (eagerly, from sw_append:
+// the scan of a new chunk then runs beside the round kernel of the previous one)
 template <int NC>
-int cansee_scan(sw_engine *e) {
-    const int first = e->n_rowed, n = e->n_events - e->n_rowed;
+int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
+    const int first = e->n_rowed, n = upto - e->n_rowed;
     if (n <= 0) return 0;
     CsParams C{};
     C.M = e->M; C.first = first; C.n = n;
@@ -220,19 +237,19 @@ int cansee_scan(sw_engine *e) {
     C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.row = e->d_row;
     C.exported = e->d_exported; C.exp_list = e->d_exp_list; C.exp_m = e->d_exp_m; C.exp_cnt = e->d_exp_cnt;
     C.last = e->d_cs_last; C.Qtab = e->d_cs_Q; C.carry = e->d_cs_carry;
-    CK(cudaMemsetAsync(e->d_exported + first, 0, (size_t)n, e->stream));
-    CK(cudaMemsetAsync(e->d_exp_cnt, 0, sizeof(int32_t) * (size_t)C.nb, e->stream));
+    CK(cudaMemsetAsync(e->d_exported + first, 0, (size_t)n, st));
+    CK(cudaMemsetAsync(e->d_exp_cnt, 0, sizeof(int32_t) * (size_t)C.nb, st));
     cudaEvent_t a = get_event(e), b = get_event(e);
-    cudaEventRecord(a, e->stream);
-    k_cs_local<NC, 1><<<C.nb, NC * 32, 0, e->stream>>>(C);
-    k_cs_collect<<<std::max(1, std::min(296, (n + 255) / 256)), 256, 0, e->stream>>>(C);
-    k_cs_boundary<NC><<<1, 1024, 0, e->stream>>>(C);
-    k_cs_local<NC, 2><<<C.nb, NC * 32, 0, e->stream>>>(C);
-    cudaEventRecord(b, e->stream);
+    cudaEventRecord(a, st);
+    k_cs_local<NC, 1><<<C.nb, NC * 32, 0, st>>>(C);
+    k_cs_collect<<<std::max(1, std::min(296, (n + 255) / 256)), 256, 0, st>>>(C);
+    k_cs_boundary<NC><<<1, 1024, 0, st>>>(C);
+    k_cs_local<NC, 2><<<C.nb, NC * 32, 0, st>>>(C);
+    cudaEventRecord(b, st);
     e->spans.push_back(TimedSpan{a, b, 3});
     CK(cudaGetLastError());
     e->stats.kernel_launches += 4;
-    e->n_rowed = e->n_events;
+    e->n_rowed = upto;
     return 0;
 }
 
@@ -268,7 +285,10 @@ template <int NC, bool UNIT>
 int divide_round_batch(sw_engine *e, const DivParams &D) {
     RbParams R{};
     R.M = e->M; R.first = D.first; R.n = D.n; R.Rcap = e->Rcap;
-    const int grid = e->n_sm;
+    // a few SMs stay free for the can_see scan of the next chunk, which runs beside this kernel (SW_RB_FREE_SMS)
+    int free_sms = 16;
+    if (const char *v = getenv("SW_RB_FREE_SMS")) free_sms = std::max(0, atoi(v));
+    const int grid = std::max(e->n_sm / 2, e->n_sm - free_sms);
     R.L = std::max(1, std::min(RB_LMAX, grid * (RB_THREADS / 32) / e->M));
     R.maxmiss = RB_MAXMISS;
     R.epoch = ++e->rb_epoch;
@@ -347,7 +367,6 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&e->ev_append, cudaEventDisableTiming));
         const size_t cap = e->cap, RM = (size_t)e->Rcap * M;
         CK(cudaMallocHost((void **)&e->h_height, sizeof(int32_t) * cap));
         CK(cudaMallocHost((void **)&e->h_seq, sizeof(int32_t) * cap));
@@ -387,7 +406,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
 void sw_destroy(sw_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->stream) { wait_appends(e, -1); cudaStreamSynchronize(e->stream); }
     fold_spans(e);
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
@@ -402,7 +421,6 @@ void sw_destroy(sw_engine *e) {
     if (e->h_newc) cudaFreeHost(e->h_newc);
     if (e->h_height) cudaFreeHost(e->h_height);
     if (e->h_seq) cudaFreeHost(e->h_seq);
-    if (e->ev_append) cudaEventDestroy(e->ev_append);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -411,6 +429,7 @@ void sw_destroy(sw_engine *e) {
 int sw_reset(sw_engine *e) {
     if (!e) return SW_E_ARG;
     CK(cudaSetDevice(e->device));
+    if (wait_appends(e, -1) < 0) return SW_E_CUDA;
     CK(cudaStreamSynchronize(e->stream));
     fold_spans(e);
     e->h_creator.clear();
@@ -422,6 +441,7 @@ int sw_reset(sw_engine *e) {
 int sw_rewind(sw_engine *e) {
     if (!e) return SW_E_ARG;
     CK(cudaSetDevice(e->device));
+    if (wait_appends(e, -1) < 0) return SW_E_CUDA;
     CK(cudaStreamSynchronize(e->stream));
     fold_spans(e);
     return reset_state(e, true);
@@ -489,11 +509,19 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
     CK(cudaMemcpyAsync(e->d_sig + (size_t)base * 64, sig, (size_t)64 * n, cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync(e->d_seq + base, e->h_seq + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync(e->d_height + base, e->h_height + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
-    CK(cudaEventRecord(e->ev_append, cs));
-    CK(cudaStreamWaitEvent(e->stream, e->ev_append, 0));
+    // rows are up to date and the batch is big: scan it now, beside the kernels of the previous chunk
+    const bool eager = e->cansee_scan && e->n_rowed == base && n >= 4096;
     e->stats.h2d_bytes += (i64)n * (5 * 4 + 8 + 64);
     e->stats.events += n;
     e->n_events += n;
+    if (eager) {
+        int rc2 = e->NC == 1 ? cansee_scan<1>(e, cs, e->n_events) : cansee_scan<2>(e, cs, e->n_events);
+        if (rc2 < 0) return rc2;
+    }
+    // the compute stream waits for this batch only when a call first touches it (wait_appends)
+    cudaEvent_t done = get_event(e);
+    CK(cudaEventRecord(done, cs));
+    e->appends.push_back({base, done});
     return SW_OK;
 }
 
@@ -503,6 +531,7 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     if (first != e->n_divided) return fail(e, SW_E_ARG, "divide_rounds: first=%d but %d events are divided (events must arrive in order)", first, e->n_divided);
     if (first + n > e->n_events) return fail(e, SW_E_KEY, "divide_rounds: events [%d,%d) not appended", first, first + n);
     CK(cudaSetDevice(e->device));
+    if (wait_appends(e, first + n) < 0) return SW_E_CUDA;
     DivParams P{};
     P.M = e->M; P.first = first; P.n = n; P.Rcap = e->Rcap;
     P.p0 = e->d_p0; P.p1 = e->d_p1; P.creator = e->d_creator;
@@ -513,7 +542,7 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
     Q.coin = e->d_coin; Q.sig = e->d_sig; Q.unit = e->unit ? 1 : 0;
     if (e->cansee_scan && first + n > e->n_rowed) {
-        int rc = e->NC == 1 ? cansee_scan<1>(e) : cansee_scan<2>(e);
+        int rc = e->NC == 1 ? cansee_scan<1>(e, e->stream, e->n_events) : cansee_scan<2>(e, e->stream, e->n_events);
         if (rc < 0) return rc;
     }
     {
@@ -634,6 +663,7 @@ int sw_n_transactions(const sw_engine *e) { return e ? e->n_tx : SW_E_ARG; }
 int sw_sync(sw_engine *e) {
     if (!e) return SW_E_ARG;
     CK(cudaSetDevice(e->device));
+    if (wait_appends(e, -1) < 0) return SW_E_CUDA;
     CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     fold_spans(e);
@@ -659,6 +689,7 @@ int sw_stats(sw_engine *e, sw_stats_t *out) {
         if (first + n > (LIMIT)) return fail(e, SW_E_KEY, #NAME ": [%d,%d) out of range", first, first + n); \
         if (n == 0) return SW_OK;                                                                    \
         CK(cudaSetDevice(e->device));                                                                \
+        if (wait_appends(e, -1) < 0) return SW_E_CUDA;                                               \
         CK(cudaMemcpyAsync(out, (SRC) + (size_t)first * (WIDTH), sizeof(TYPE) * (size_t)n * (WIDTH), \
                            cudaMemcpyDeviceToHost, e->stream));                                     \
         CK(cudaStreamSynchronize(e->stream));                                                        \
