@@ -72,8 +72,10 @@ const char *sw_last_error(const sw_engine *e);   /* e may be NULL: last create e
  * p0/p1 = self/other parent index (-1,-1 for a root: ev.p == ()), creator,
  * t = Event.t (swirld.py:91), sig = Event.s, 64 bytes each (swirld.py:92).
  * Checks what is_valid_event checks on the graph shape (swirld.py:104-108) and
- * the fork-free contract; copies the columns to the device.  The copies run on the
- * engine's copy stream beside the kernels of earlier calls: when the columns are in
+ * the fork-free contract; copies the columns to the device and, for a batch of 4096
+ * events or more, starts their can_see rows (swirld.py:203-205, 220) right away.  Both run
+ * on the engine's copy stream beside the kernels of earlier calls (a caller that appends a
+ * chunk or two ahead of its sw_divide_rounds calls hides them completely): when the columns are in
  * page-locked host memory they must stay unchanged until the next synchronising call
  * (sw_decide_fame, sw_find_order, sw_sync, any sw_get_*); pageable memory is staged
  * before the call returns. */
