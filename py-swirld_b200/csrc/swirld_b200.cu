@@ -542,8 +542,25 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
     Q.coin = e->d_coin; Q.sig = e->d_sig; Q.unit = e->unit ? 1 : 0;
     if (e->cansee_scan && first + n > e->n_rowed) {
-        int rc = e->NC == 1 ? cansee_scan<1>(e, e->stream, e->n_events) : cansee_scan<2>(e, e->stream, e->n_events);
+        // the rows this call needs, on the compute stream ...
+        int rc = e->NC == 1 ? cansee_scan<1>(e, e->stream, first + n) : cansee_scan<2>(e, e->stream, first + n);
         if (rc < 0) return rc;
+        // ... and those of everything appended beyond it on the copy stream, beside the round kernels
+        if (e->n_events - e->n_rowed >= 4096) {
+            cudaEvent_t lazy_done = get_event(e);
+            CK(cudaEventRecord(lazy_done, e->stream));
+            CK(cudaStreamWaitEvent(e->copy_stream, lazy_done, 0));      // (the scans share their work lists and the carry)
+            e->pool.push_back(lazy_done);
+            const int base = e->n_rowed;
+            rc = e->NC == 1 ? cansee_scan<1>(e, e->copy_stream, e->n_events) : cansee_scan<2>(e, e->copy_stream, e->n_events);
+            if (rc < 0) return rc;
+            cudaEvent_t done = get_event(e);
+            CK(cudaEventRecord(done, e->copy_stream));
+            e->appends.push_back({base, done});
+        } else if (e->n_events > e->n_rowed) {
+            rc = e->NC == 1 ? cansee_scan<1>(e, e->stream, e->n_events) : cansee_scan<2>(e, e->stream, e->n_events);
+            if (rc < 0) return rc;
+        }
     }
     {
         Span sp(e, 0);
