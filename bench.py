@@ -28,7 +28,9 @@ Trace: generator G1 (reference-sim gossip), seed 1 + rank.
             B1(M) = 12M + 12 bytes per event), the bandwidth-bound part of the path.
 `cpu_baseline` / --impl reference: the reference is pure Python and cannot travel to
             the GPU box, so the CPU arm is the literal C restatement oracle/
-            (kind "port"), single-threaded like the reference (README.md:27-28).
+            (kind "port"), single-threaded per node-view like the reference
+            (README.md:27-28); at N > 1 it runs the N replicas of the GPU arm's workload in
+            N parallel processes (cores = N).
 
 N > 1: one process per GPU (torchrun), each rank runs an independent node-view
 (its own trace, seed 1 + rank) -- the path has no cross-GPU exchange at M <= 64
@@ -157,31 +159,49 @@ def run_cpu_pass(tr, K, limit=None):
     return n, res["t_divide_rounds"] + res["t_decide_fame"], res["t_find_order"]
 
 
-def bench_reference(args, wl, rank, world):
-    if rank != 0:
-        return
-    tr = make_trace(wl, 1)
-    # bounded sample: the whole trace when the port finishes it in well under a minute
-    limit = None
-    for _ in range(args.warmup if args.warmup < 1 else 1):
+def _reference_replica(job):
+    """One node-view through the CPU port (runs in its own process when world > 1)."""
+    wl, seed, steps, warm = job
+    tr = make_trace(wl, seed)
+    if warm:
         run_cpu_pass(tr, wl["K"], limit=min(tr.N, 50000))
-    tot_e, tot_s = 0, 0.0
-    t_fo = 0.0
-    for _ in range(args.steps):
-        n, s, fo = run_cpu_pass(tr, wl["K"], limit)
+    t0 = time.perf_counter()
+    tot_e, tot_s, t_fo = 0, 0.0, 0.0
+    for _ in range(steps):
+        n, s, fo = run_cpu_pass(tr, wl["K"], None)
         tot_e += n
         tot_s += s
         t_fo += fo
-    v = tot_e / tot_s
+    return tot_e, tot_s, t_fo, time.perf_counter() - t0
+
+
+def bench_reference(args, wl, rank, world):
+    """The CPU arm on the workload of the GPU arm: `world` independent node-views (replicas), one host core
+    each -- the reference is single-threaded per node (README.md:27-28), so replicas are the only way it
+    can use more cores."""
+    if rank != 0:
+        return
+    jobs = [(wl, rank_seed(r), args.steps, args.warmup >= 1) for r in range(world)]
+    if world == 1:
+        res = [_reference_replica(jobs[0])]
+    else:
+        import concurrent.futures as cf
+        import multiprocessing as mp
+        with cf.ProcessPoolExecutor(world, mp_context=mp.get_context("spawn")) as ex:
+            res = list(ex.map(_reference_replica, jobs))
+    tot_e = sum(r[0] for r in res)
+    slow = max(r[1] for r in res)                # the job is as slow as its slowest replica
+    t_fo = max(r[2] for r in res)
+    v = tot_e / slow
     line = {
         "impl": "reference", "metric": "events/sec divide_rounds+decide_fame", "value": v, "unit": "events/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * slow / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": workload_config(wl, world),
-        "cpu_baseline": {"value": v, "unit": "events/s", "cores": 1, "kind": "port",
-                         "sample": "full trace, %d events x %d passes, oracle/swirld_oracle.c (literal C restatement; "
-                                   "the Python reference cannot travel to the GPU box), host has %d cpus"
-                                   % (tr.N, args.steps, os.cpu_count())},
+        "cpu_baseline": {"value": v, "unit": "events/s", "cores": world, "kind": "port",
+                         "sample": "full trace, %d events x %d passes per replica, %d replica(s) in parallel processes, "
+                                   "oracle/swirld_oracle.c (literal C restatement; the Python reference cannot travel to "
+                                   "the GPU box), host has %d cpus" % (wl["N"], args.steps, world, os.cpu_count())},
         "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "find_order_events_per_s": tot_e / t_fo if t_fo > 0 else None,
     }
