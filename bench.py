@@ -386,7 +386,9 @@ def bench_ours(args, wl, rank, world, local_rank):
             "config": workload_config(wl, world),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "events/s",
-                    "h2d_bytes_per_step": int(N * (4 * 4 + 8 + 64)), "d2h_bytes_per_step": int(N * 6 + 64 * len(sched)),
+                    # counted by the library from the copies it issued in the last step (event columns incl. the
+                    # derived seq/height columns; results + per-call scalars)
+                    "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
                     "ms_per_step": e2e_ms_max / e2e_steps,
                     "kernel_ms_last_step": {"divide_rounds": st_e2e["ms_divide_rounds"], "can_see_scan": st_e2e["ms_can_see"],
                                             "rounds_kernel": st_e2e["ms_rounds_kernel"], "decide_fame": st_e2e["ms_decide_fame"]},

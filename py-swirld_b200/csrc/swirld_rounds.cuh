@@ -18,21 +18,21 @@
 // witness changes nothing, because seeing a skipping member's event already implies a
 // higher round.  tests/test_rounds_model.py keeps the executable proof against the oracle.)
 //
-// So one cooperative kernel advances all chains round by round: in every step each member
-// chain that is waiting at the lowest open round r tests P_r on its next L pending events
-// (one warp per event, all SMs), a grid barrier follows, and every CTA applies the same
-// bookkeeping: events before the chain's first hit are final at round r, the first hit opens
-// round r+1 for that chain (Wf_{r+1}[c]).  The depth of the computation is the number of
-// ROUNDS in the chunk (~1 per 690 events at 64 members), not the number of DAG levels.
-//
-// S_r(k) = {c_ : row(k)[c_] >= Wf_r[c_] >= 0} of an event k is cached per event with the
-// round it was computed for (a 16-byte {mask, mask ^ key(r)} entry, so a torn or stale read
-// is detected and simply recomputed).
+// So one cooperative kernel advances all chains round by round.  A step (= one round r):
+//   a  every warp computes the masks S_r(k) = {c_ : row(k)[c_] >= Wf_r[c_] >= 0} of up to two events k of
+//      the members' ranges [Wf_r[c], end of c's pending window) into the per-event cache `sc`
+//      (16-byte entries {mask, mask ^ key(r, launch)}: a stale or torn entry fails the key test);
+//   b  one warp per (chain, pending position) tests P_r: it gathers the <= 64 masks of the events its row
+//      points at -- polling the entries that are still being produced, there is no barrier between a
+//      and b --, transposes the 64x64 bit matrix with warp shuffles and counts its columns; the first
+//      hit of a chain is kept by atomicMin;
+//   c  ONE grid barrier, then every CTA applies the same bookkeeping: events before the chain's first hit
+//      are final at round r, the hit opens round r+1 for the chain (Wf_{r+1}[c]).
+// The depth of the computation is the number of ROUNDS in the chunk (~1 per 690 events at 64 members),
+// not the number of DAG levels.  An event far ahead of the windows (it sees events whose masks nobody
+// prepared) is left untested and truncates its chain's window for this step.
 #pragma once
-#include <cooperative_groups.h>
 #include "swirld_kernels.cuh"
-
-namespace cg = cooperative_groups;
 
 #define RB_WR 32            // rounds of Wf mirrored in shared memory
 #define RB_LMAX 64          // pending events tested per chain and step (at most)
