@@ -70,7 +70,7 @@ struct sw_engine {
     // find_order
     int32_t *d_lastord = nullptr, *d_tx = nullptr, *d_idx = nullptr, *d_batch_ev = nullptr,
             *d_batch_seg = nullptr, *d_seg_start = nullptr, *d_seg_fw = nullptr, *d_seg_nf = nullptr,
-            *d_perm = nullptr, *d_rounds_in = nullptr;
+            *d_perm = nullptr, *d_rounds_in = nullptr, *d_plan = nullptr;
     uint8_t *d_seg_white = nullptr;
     double *d_ts = nullptr;
     u64 *d_key = nullptr;
@@ -415,7 +415,7 @@ void sw_destroy(sw_engine *e) {
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
                     e->d_batch_ev, e->d_batch_seg, e->d_perm, e->d_ts, e->d_key, e->d_seg_start, e->d_seg_fw,
-                    e->d_seg_nf, e->d_seg_white, e->d_rounds_in, e->d_flush};
+                    e->d_seg_nf, e->d_seg_white, e->d_rounds_in, e->d_plan, e->d_flush};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (e->h_scal) cudaFreeHost(e->h_scal);
     if (e->h_newc) cudaFreeHost(e->h_newc);
@@ -542,25 +542,11 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
     Q.coin = e->d_coin; Q.sig = e->d_sig; Q.unit = e->unit ? 1 : 0;
     if (e->cansee_scan && first + n > e->n_rowed) {
-        // the rows this call needs, on the compute stream ...
-        int rc = e->NC == 1 ? cansee_scan<1>(e, e->stream, first + n) : cansee_scan<2>(e, e->stream, first + n);
+        // rows are behind (small appends, or after sw_rewind): scan everything appended so far, here.
+        // (Scanning only [n_rowed, first+n) here and the rest on the copy stream beside the round kernels was
+        // measured: 1% faster on average at C3, but with a visible run-to-run spread.)
+        int rc = e->NC == 1 ? cansee_scan<1>(e, e->stream, e->n_events) : cansee_scan<2>(e, e->stream, e->n_events);
         if (rc < 0) return rc;
-        // ... and those of everything appended beyond it on the copy stream, beside the round kernels
-        if (e->n_events - e->n_rowed >= 4096) {
-            cudaEvent_t lazy_done = get_event(e);
-            CK(cudaEventRecord(lazy_done, e->stream));
-            CK(cudaStreamWaitEvent(e->copy_stream, lazy_done, 0));      // (the scans share their work lists and the carry)
-            e->pool.push_back(lazy_done);
-            const int base = e->n_rowed;
-            rc = e->NC == 1 ? cansee_scan<1>(e, e->copy_stream, e->n_events) : cansee_scan<2>(e, e->copy_stream, e->n_events);
-            if (rc < 0) return rc;
-            cudaEvent_t done = get_event(e);
-            CK(cudaEventRecord(done, e->copy_stream));
-            e->appends.push_back({base, done});
-        } else if (e->n_events > e->n_rowed) {
-            rc = e->NC == 1 ? cansee_scan<1>(e, e->stream, e->n_events) : cansee_scan<2>(e, e->stream, e->n_events);
-            if (rc < 0) return rc;
-        }
     }
     {
         Span sp(e, 0);
@@ -630,11 +616,11 @@ int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
     for (int r : rs) if (r < 0 || r >= e->Rcap) return fail(e, SW_E_KEY, "find_order: unknown round %d", r);
     if (n > e->seg_cap) {
         int nc = std::max(n, std::max(64, 2 * e->seg_cap));
-        for (void *p : {(void *)e->d_seg_start, (void *)e->d_seg_fw, (void *)e->d_seg_nf, (void *)e->d_seg_white, (void *)e->d_rounds_in})
+        for (void *p : {(void *)e->d_seg_start, (void *)e->d_seg_fw, (void *)e->d_seg_nf, (void *)e->d_seg_white, (void *)e->d_rounds_in, (void *)e->d_plan})
             if (p) cudaFree(p);
         CK(dalloc(&e->d_seg_start, (size_t)nc + 1)); CK(dalloc(&e->d_seg_fw, (size_t)nc * 64));
         CK(dalloc(&e->d_seg_nf, (size_t)nc)); CK(dalloc(&e->d_seg_white, (size_t)nc * 64));
-        CK(dalloc(&e->d_rounds_in, (size_t)nc));
+        CK(dalloc(&e->d_rounds_in, (size_t)nc)); CK(dalloc(&e->d_plan, (size_t)nc * 64 * 8));
         e->seg_cap = nc;
     }
     CK(cudaMemcpyAsync(e->d_rounds_in, rs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
@@ -644,13 +630,16 @@ int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
     P.stake = e->d_stake; P.tot = e->tot; P.lastord = e->d_lastord; P.batch_ev = e->d_batch_ev; P.batch_seg = e->d_batch_seg;
     P.seg_start = e->d_seg_start; P.seg_fw = e->d_seg_fw; P.seg_nf = e->d_seg_nf; P.seg_white = e->d_seg_white;
     P.ts = e->d_ts; P.key = e->d_key; P.perm = e->d_perm; P.tx = e->d_tx; P.idx = e->d_idx; P.tx_base = e->n_tx; P.scal = e->d_scal;
+    P.plan = e->d_plan; P.plan_stride = e->seg_cap * 64;
     cudaEvent_t a = get_event(e), b = get_event(e);
     cudaEventRecord(a, e->stream);
-    k_order_plan<<<1, 1024, 0, e->stream>>>(P);
+    k_order_rounds<<<n, 1024, 0, e->stream>>>(P);
+    k_order_cuts<<<1, 64, 0, e->stream>>>(P);
+    k_order_list<<<std::max(1, std::min(4 * e->n_sm, (n * 64 + 255) / 256)), 256, 0, e->stream>>>(P);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));      // rs (host vector) was consumed by the copy above
-    e->stats.kernel_launches += 1;
+    e->stats.kernel_launches += 3;
     e->stats.h2d_bytes += sizeof(int32_t) * n;
     e->stats.d2h_bytes += sizeof(int32_t) * SC_COUNT;
     int rc = device_error(e);

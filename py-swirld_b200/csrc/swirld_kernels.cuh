@@ -298,6 +298,10 @@ struct OrderParams {
     int32_t *idx;                // [cap]
     int tx_base;
     int32_t *scal;
+    // plan scratch, 8 planes of [plan_stride] ints indexed by segment*64 + chain (or witness slot):
+    // 0 thr, 1 reach over all famous witnesses, 2 seq[thr], 3 seq[reach], 4 creator of witness slot, 5 cut, 6 count, 7 offset
+    int32_t *plan;
+    int plan_stride;
 };
 
 // Plan: for each new consensus round (ascending, sequential because the "not yet
@@ -307,99 +311,147 @@ struct OrderParams {
 // exactly the not-yet-ordered events x with x <= max_{w in f_w & tbd} row(w)[c], and
 // "received" (swirld.py:291-293) is monotone along the chain, so the newly ordered
 // events of chain c are (lastord[c], min(reach, received-threshold)].
-__global__ void __launch_bounds__(1024, 1) k_order_plan(OrderParams P) {
+#define PLAN(k) (P.plan + (size_t)(k) * P.plan_stride)
+
+// A: everything about a consensus round that does not depend on what earlier rounds ordered -- one CTA
+// per round: famous witnesses, whitening XOR, and per member chain the received-threshold `thr` and the
+// reach over ALL famous witnesses (the usual case: none of them is ordered yet).
+__global__ void __launch_bounds__(1024, 1) k_order_rounds(OrderParams P) {
     __shared__ int fw[64];
-    __shared__ int cnts[64];
     __shared__ int nf_s;
     __shared__ unsigned ball[2];
     __shared__ int mat[64][64];          // mat[i][c] = row(fw[i])[c]
     __shared__ i64 st[64];               // stake of fw[i]'s creator
-    __shared__ int tbd_s[64];            // fw[i] not yet ordered
     __shared__ int U_s[64], thr_s[64];
-    const int tid = threadIdx.x, M = P.M;
+    const int tid = threadIdx.x, M = P.M, si = blockIdx.x;
+    const int r = P.rounds[si];
+    int w = -1, fam = -1;
+    if (tid < 64) {
+        if (tid < M && r >= 0 && r < P.Rcap) { w = P.W[(size_t)r * M + tid]; fam = P.famous[(size_t)r * M + tid]; }
+        if (w >= 0 && fam < 0) atomicMin(&P.scal[SC_ERR], -3);   // self.famous[w] KeyError, :284
+        const unsigned b0 = __ballot_sync(0xffffffffu, w >= 0 && fam == 1);
+        if ((tid & 31) == 0) ball[tid >> 5] = b0;
+        U_s[tid] = -1; thr_s[tid] = -1;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const bool isf = w >= 0 && fam == 1;
+        const int pos = (tid >= 32 ? __popc(ball[0]) : 0) + __popc(ball[tid >> 5] & ((1u << (tid & 31)) - 1));
+        if (isf) {
+            fw[pos] = w;
+            const int cw = P.creator[w];
+            st[pos] = P.stake[cw];
+            PLAN(4)[si * 64 + pos] = cw;
+        }
+        if (tid == 0) nf_s = __popc(ball[0]) + __popc(ball[1]);
+    }
+    __syncthreads();
+    const int nf = nf_s;
+    for (int i = tid; i < nf * 64; i += 1024) {
+        const int fi = i >> 6, c = i & 63;
+        mat[fi][c] = c < M ? P.row[(size_t)fw[fi] * M + c] : -1;
+    }
+    if (tid < 64) {   // white = XOR of the famous witnesses' signatures, byte tid
+        uint8_t x = 0;
+        for (int i = 0; i < nf; i++) x ^= P.sig[(size_t)fw[i] * 64 + tid];
+        P.seg_white[(size_t)si * 64 + tid] = x;
+        P.seg_fw[(size_t)si * 64 + tid] = tid < nf ? fw[tid] : -1;
+        if (tid == 0) P.seg_nf[si] = nf;
+    }
+    __syncthreads();
+    {   // per chain c: reach and received-threshold, 16 thread groups x 64 chains
+        const int c = tid & 63, grp = tid >> 6;
+        int bestU = -1, bestT = -1;
+        for (int i = grp; i < nf; i += 16) {
+            const int v = mat[i][c];
+            bestU = max(bestU, v);
+            if (v > bestT) {     // is v seen by more than half the stake?  (:291-293)
+                i64 acc = 0;
+                for (int k = 0; k < nf; k++)
+                    if (mat[k][c] >= v) acc += st[k];
+                if (2 * acc > P.tot) bestT = v;
+            }
+        }
+        if (bestU >= 0) atomicMax(&U_s[c], bestU);
+        if (bestT >= 0) atomicMax(&thr_s[c], bestT);
+    }
+    __syncthreads();
+    if (tid < 64) {
+        const int thr = thr_s[tid], ua = U_s[tid];
+        PLAN(0)[si * 64 + tid] = thr;
+        PLAN(1)[si * 64 + tid] = ua;
+        PLAN(2)[si * 64 + tid] = thr >= 0 ? P.seq[thr] : -1;
+        PLAN(3)[si * 64 + tid] = ua >= 0 ? P.seq[ua] : -1;
+    }
+}
+
+// B: the only sequential part -- round after round, what each chain still has to give: the events
+// (lastord[c], min(reach, thr)].  A famous witness that an earlier round already ordered does not seed
+// the search (swirld.py:288-289, `f_w & tbd`); then the reach is taken over the others.  One thread per
+// chain; the next round's vectors are fetched while this one is decided.
+__global__ void __launch_bounds__(64) k_order_cuts(OrderParams P) {
+    __shared__ int lastord_s[64], tbd_s[64], wtot[2];
+    const int c = threadIdx.x, lane = c & 31, M = P.M;
+    int lo = c < M ? P.lastord[c] : -1;
+    int loseq = lo >= 0 ? P.seq[lo] : -1;
+    lastord_s[c] = lo;
     int total = 0;
+    int thr = -1, ua = -1, sthr = -1, sua = -1, fwv = -1, cwv = 0, nf = 0;
+    auto fetch = [&](int si, int &thr_, int &ua_, int &sthr_, int &sua_, int &fw_, int &cw_, int &nf_) {
+        thr_ = PLAN(0)[si * 64 + c]; ua_ = PLAN(1)[si * 64 + c]; sthr_ = PLAN(2)[si * 64 + c]; sua_ = PLAN(3)[si * 64 + c];
+        nf_ = P.seg_nf[si];
+        fw_ = P.seg_fw[si * 64 + c];
+        cw_ = fw_ >= 0 ? PLAN(4)[si * 64 + c] : 0;
+    };
+    if (P.nrounds > 0) fetch(0, thr, ua, sthr, sua, fwv, cwv, nf);
+    __syncthreads();
     for (int si = 0; si < P.nrounds; ++si) {
-        const int r = P.rounds[si];
-        if (tid < 64) {
-            int w = -1, fam = -1;
-            if (tid < M && r >= 0 && r < P.Rcap) { w = P.W[(size_t)r * M + tid]; fam = P.famous[(size_t)r * M + tid]; }
-            if (w >= 0 && fam < 0) atomicMin(&P.scal[SC_ERR], -3);   // self.famous[w] KeyError, :284
-            const bool isf = w >= 0 && fam == 1;
-            const unsigned b0 = __ballot_sync(0xffffffffu, isf);
-            if ((tid & 31) == 0) ball[tid >> 5] = b0;
-            U_s[tid] = -1; thr_s[tid] = -1;
+        int nthr = -1, nua = -1, nsthr = -1, nsua = -1, nfw = -1, ncw = 0, nnf = 0;
+        if (si + 1 < P.nrounds) fetch(si + 1, nthr, nua, nsthr, nsua, nfw, ncw, nnf);
+        const bool ok = c >= nf || fwv > lastord_s[cwv];           // witness slot c is in tbd
+        tbd_s[c] = ok ? 1 : 0;
+        const int allok = __syncthreads_and(ok);
+        int U = ua, sU = sua;
+        if (!allok) {
+            U = -1;
+            for (int i = 0; i < nf; i++)
+                if (tbd_s[i] && c < M) U = max(U, P.row[(size_t)P.seg_fw[si * 64 + i] * M + c]);
+            sU = U >= 0 ? P.seq[U] : -1;
         }
+        const int cut = min(U, thr), scut = U <= thr ? sU : sthr;
+        const int cnt = (c < M && cut > lo) ? scut - loseq : 0;
+        int inc = cnt;                                              // offsets: chains in member order
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+        if (lane == 31) wtot[c >> 5] = inc;
         __syncthreads();
-        if (tid < 64) {
-            int w = -1, fam = -1;
-            if (tid < M && r >= 0 && r < P.Rcap) { w = P.W[(size_t)r * M + tid]; fam = P.famous[(size_t)r * M + tid]; }
-            const bool isf = w >= 0 && fam == 1;
-            const unsigned mine = ball[tid >> 5];
-            const int pos = (tid >= 32 ? __popc(ball[0]) : 0) + __popc(mine & ((1u << (tid & 31)) - 1));
-            if (isf) {
-                fw[pos] = w;
-                const int cw = P.creator[w];
-                st[pos] = P.stake[cw];
-                tbd_s[pos] = w > P.lastord[cw] ? 1 : 0;                  // w in tbd
-            }
-            if (tid == 0) nf_s = __popc(ball[0]) + __popc(ball[1]);
-        }
-        __syncthreads();
-        const int nf = nf_s;
-        for (int i = tid; i < nf * 64; i += 1024) {
-            const int fi = i >> 6, c = i & 63;
-            mat[fi][c] = c < M ? P.row[(size_t)fw[fi] * M + c] : -1;
-        }
-        if (tid < 64) {   // white = XOR of the famous witnesses' signatures, byte tid
-            uint8_t x = 0;
-            for (int i = 0; i < nf; i++) x ^= P.sig[(size_t)fw[i] * 64 + tid];
-            P.seg_white[(size_t)si * 64 + tid] = x;
-            P.seg_fw[(size_t)si * 64 + tid] = tid < nf ? fw[tid] : -1;
-            if (tid == 0) { P.seg_nf[si] = nf; P.seg_start[si] = total; }
-        }
-        __syncthreads();
-        {   // per chain c: reach U[c] and received-threshold thr[c], 16 thread groups x 64 chains
-            const int c = tid & 63, grp = tid >> 6;
-            int bestU = -1, bestT = -1;
-            for (int i = grp; i < nf; i += 16) {
-                const int v = mat[i][c];
-                if (tbd_s[i]) bestU = max(bestU, v);
-                if (v > bestT) {     // is v seen by more than half the stake?  (:291-293)
-                    i64 acc = 0;
-                    for (int k = 0; k < nf; k++)
-                        if (mat[k][c] >= v) acc += st[k];
-                    if (2 * acc > P.tot) bestT = v;
-                }
-            }
-            if (bestU >= 0) atomicMax(&U_s[c], bestU);
-            if (bestT >= 0) atomicMax(&thr_s[c], bestT);
-        }
-        __syncthreads();
-        int cnt = 0, cut = -1;
-        if (tid < M) {
-            cut = min(U_s[tid], thr_s[tid]);
-            const int lo = P.lastord[tid];
-            if (cut > lo) cnt = P.seq[cut] - (lo >= 0 ? P.seq[lo] : -1);
-        }
-        if (tid < 64) cnts[tid] = cnt;
-        __syncthreads();
-        int tot_here = 0;
-        for (int i = 0; i < 64; i++) tot_here += cnts[i];
-        if (tid < 64 && cnt > 0) {
-            int off = total;
-            for (int i = 0; i < tid; i++) off += cnts[i];
-            int x = cut;
-            for (int j = 0; j < cnt; j++) {
-                P.batch_ev[off + j] = x;
-                P.batch_seg[off + j] = si;
-                x = P.p0[x];
-            }
-            P.lastord[tid] = cut;
-        }
-        total += tot_here;
+        const int off = total + (c >= 32 ? wtot[0] : 0) + inc - cnt;
+        PLAN(5)[si * 64 + c] = cnt > 0 ? cut : -1;
+        PLAN(6)[si * 64 + c] = cnt;
+        PLAN(7)[si * 64 + c] = off;
+        if (c == 0) P.seg_start[si] = total;
+        total += wtot[0] + wtot[1];
+        if (cnt > 0) { lo = cut; loseq = scut; lastord_s[c] = cut; }
+        thr = nthr; ua = nua; sthr = nsthr; sua = nsua; fwv = nfw; cwv = ncw; nf = nnf;
         __syncthreads();
     }
-    if (tid == 0) { P.seg_start[P.nrounds] = total; P.scal[SC_BATCH] = total; }
+    if (c < M) P.lastord[c] = lo;
+    if (c == 0) { P.seg_start[P.nrounds] = total; P.scal[SC_BATCH] = total; }
+}
+
+// C: list the ordered events of every (round, chain): from the cut down the self-parent chain
+__global__ void k_order_list(OrderParams P) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nrounds * 64; i += gridDim.x * blockDim.x) {
+        const int cnt = PLAN(6)[i];
+        if (cnt <= 0) continue;
+        int x = PLAN(5)[i];
+        const int off = PLAN(7)[i], si = i >> 6;
+        for (int j = 0; j < cnt; j++) {
+            P.batch_ev[off + j] = x;
+            P.batch_seg[off + j] = si;
+            x = P.p0[x];
+        }
+    }
 }
 
 // Consensus timestamp and sort key of each newly ordered event (swirld.py:295-306):
