@@ -417,10 +417,8 @@ def bench_ours(args, wl, rank, world, local_rank):
                 "bound": "hbm", "kernel": "k_cs_local + k_cs_collect + k_cs_boundary + k_cs_fix (blocked max-plus scan)",
                 "achieved": cs_achieved, "peak": peak, "unit": "GB/s", "frac": cs_achieved / peak,
                 "algorithmic_bytes_per_event": can_see_bytes_per_event(M), "ms_per_step": ms_cs / args.steps,
-                "note": "summed launch durations of the scan kernels; the first divide_rounds of a step scans its own "
-                        "chunk on the compute stream and everything appended beyond it on the copy stream, BESIDE the "
-                        "round kernels, which stretches these kernels (alone: 1.06 ms per 1M events = 11% of the peak, "
-                        "profiles/r01c_ncu_full.md)"},
+                "note": "the resident leg scans all appended events in the first divide_rounds call of a step (the "
+                        "end-to-end leg scans chunk by chunk, beside the round kernel of the previous chunk)"},
             "roofline_path": {"bound": "hbm", "what": "all kernels of divide_rounds + decide_fame, SURVEY.md 8d B(M)",
                               "achieved": path_achieved, "peak": peak, "unit": "GB/s", "frac": path_achieved / peak,
                               "algorithmic_bytes_per_event": algorithmic_bytes_per_event(M)},
