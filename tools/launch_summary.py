@@ -16,8 +16,8 @@ for i in fills:
     else: groups.append([i])
 out = ['# Launch list of `python bench.py --steps 2 --warmup 1` (64 members x 1M events, K=65536), round 1 final', '',
        '`ncu --metrics gpu__time_duration.sum --clock-control none -c 1500` (raw list: r01c_launches_c3.csv).  Per-launch times',
-       'under ncu are cold-cache and SERIALISED (the can_see scan that normally runs beside the round kernel on the copy',
-       'stream is timed alone here): read the shares, the absolute step time is bench.py\'s.', '']
+       'under ncu are cold-cache and SERIALISED (in the end-to-end step the can_see scan normally runs beside the round',
+       'kernel, on the copy stream; here it is timed alone): read the shares, the absolute step time is bench.py\'s.', '']
 
 
 def table(title, lo, hi):
