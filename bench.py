@@ -62,7 +62,7 @@ WORKLOADS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at c3 (65536 events), from the committed
 # ncu --set full captures under profiles/ (see profiles/README.md)
-ROUNDS_DRAM_BYTES_PER_LAUNCH = 18547968 + 15616       # k_rounds_batch (profiles/r01c_ncu_full.md)
+ROUNDS_DRAM_BYTES_PER_LAUNCH = 18547712 + 2816        # k_rounds_batch (profiles/r01c_ncu_full.md)
 WALKER_DRAM_BYTES_PER_LAUNCH = 2365952 + 2083072      # k_divide_levels (SW_DIVIDE_IMPL=4)
 
 
