@@ -159,16 +159,26 @@ def run_cpu_pass(tr, K, limit=None):
     return n, res["t_divide_rounds"] + res["t_decide_fame"], res["t_find_order"]
 
 
+def reference_sample_events(wl, steps):
+    """Events per step of the CPU arm: the whole trace when the run stays within about a minute of CPU work
+    (the port does ~2e5 events/s on one core), else a prefix of whole chunks."""
+    budget = int(60 * 2.0e5 / max(1, steps))
+    if budget >= wl["N"]:
+        return wl["N"]
+    return max(wl["K"], budget // wl["K"] * wl["K"])
+
+
 def _reference_replica(job):
     """One node-view through the CPU port (runs in its own process when world > 1)."""
     wl, seed, steps, warm = job
     tr = make_trace(wl, seed)
+    limit = reference_sample_events(wl, steps)
     if warm:
         run_cpu_pass(tr, wl["K"], limit=min(tr.N, 50000))
     t0 = time.perf_counter()
     tot_e, tot_s, t_fo = 0, 0.0, 0.0
     for _ in range(steps):
-        n, s, fo = run_cpu_pass(tr, wl["K"], None)
+        n, s, fo = run_cpu_pass(tr, wl["K"], limit)
         tot_e += n
         tot_s += s
         t_fo += fo
@@ -199,9 +209,10 @@ def bench_reference(args, wl, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": workload_config(wl, world),
         "cpu_baseline": {"value": v, "unit": "events/s", "cores": world, "kind": "port",
-                         "sample": "full trace, %d events x %d passes per replica, %d replica(s) in parallel processes, "
+                         "sample": "first %d of %d events x %d passes per replica, %d replica(s) in parallel processes, "
                                    "oracle/swirld_oracle.c (literal C restatement; the Python reference cannot travel to "
-                                   "the GPU box), host has %d cpus" % (wl["N"], args.steps, world, os.cpu_count())},
+                                   "the GPU box), host has %d cpus" % (reference_sample_events(wl, args.steps), wl["N"],
+                                                                      args.steps, world, os.cpu_count())},
         "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "find_order_events_per_s": tot_e / t_fo if t_fo > 0 else None,
     }
