@@ -207,3 +207,14 @@ def test_append_everything_first(M, N, K, gen):
         assert np.array_equal(o["oracle"].can_see(), e.can_see()), "can_see differs (pass %d)" % rep
         r = e.results()
         assert np.array_equal(o["famous"], r["famous"]) and np.array_equal(o["witness"], r["witness"])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_find_order_with_already_ordered_famous_witness(seed):
+    """Traces on which some consensus round has a famous witness that an earlier round already ordered
+    (tests/test_order_model.py counts them): k_order_cuts must take the reach over the other witnesses."""
+    from swirld_b200 import traces
+    tr = traces.adversarial(8, 4000, seed, 0.02, 0.5)
+    o = orc.run_oracle(tr, 37)
+    r = _run(tr, 37)
+    assert_same(o, r, what=tr.name)
