@@ -90,7 +90,7 @@ def scan_launch(tr, first, n, B, row, carry, stats):
 
 
 @pytest.mark.parametrize("M,N,B,chunks", [(8, 600, 64, [600]), (8, 600, 64, [100, 200, 300]),
-                                          (16, 2000, 128, [700, 1300]), (16, 2500, 512, [2500]), (5, 200, 16, [1] * 200)])
+                                          (16, 2000, 128, [700, 1300]), (16, 2500, 512, [2500]), (5, 200, 16, [1] * 200), (80, 4000, 512, [1500, 2500])])
 @pytest.mark.parametrize("gen", ["gossip", "adversarial", "tick"])
 def test_blocked_scan_equals_oracle(M, N, B, chunks, gen):
     tr = getattr(traces, gen)(M, N, 3)

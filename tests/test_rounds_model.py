@@ -78,7 +78,9 @@ class RoundBatch:
     ("gossip", 4, 600, [600], None, 8), ("gossip", 4, 400, [1] * 400, None, 4),
     ("gossip", 8, 1500, [100] * 15, None, 8), ("adversarial", 8, 1500, [250] * 6, None, 8),
     ("tick", 16, 2000, [700, 1300], None, 8), ("gossip", 7, 1507, [11] * 137, [1, 1, 2, 1, 1, 1, 0], 8),
-    ("gossip", 64, 3000, [1200, 1800], None, 18)])
+    ("gossip", 64, 3000, [1200, 1800], None, 18),
+    # beyond this build's 64 members: the predicate does not care (member masks become multi-word)
+    ("gossip", 96, 7000, [3000, 4000], None, 24), ("adversarial", 130, 9000, [9000], None, 16)])
 def test_round_batch_equals_oracle(gen, M, N, chunks, stake, L):
     tr = getattr(traces, gen)(M, N, 3)
     o = orc.Oracle(M, stake)
