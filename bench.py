@@ -425,7 +425,7 @@ def bench_ours(args, wl, rank, world, local_rank):
                                   "accounting in profiles/ and tools/rounds_cycles.py") if batch else
                                  "latency/issue-bound: one CTA walks ~53.7k dependent levels per 1M events at M=64"},
             "roofline_can_see": None if cs_achieved is None else {
-                "bound": "hbm", "kernel": "k_cs_local + k_cs_collect + k_cs_boundary + k_cs_fix (blocked max-plus scan)",
+                "bound": "hbm", "kernel": "k_cs_local<.,1> + k_cs_collect + k_cs_boundary + k_cs_local<.,2> (blocked max-plus scan)",
                 "achieved": cs_achieved, "peak": peak, "unit": "GB/s", "frac": cs_achieved / peak,
                 "algorithmic_bytes_per_event": can_see_bytes_per_event(M), "ms_per_step": ms_cs / args.steps,
                 "note": "the resident leg scans all appended events in the first divide_rounds call of a step (the "

@@ -40,7 +40,7 @@ table('resident step (timed step 1)', groups[1][-1] + 1, groups[2][0])
 # an end-to-end step: the last interval between two fill groups that holds no find_order kernel
 for a, b in reversed(list(zip(groups[:-1], groups[1:]))):
     names = {k for k, v, g in seq[a[-1] + 1:b[0]]}
-    if 'k_rounds_batch<2, 1>' in names and 'k_order_plan' not in names and b[0] - a[-1] > 150:
+    if 'k_rounds_batch<2, 1>' in names and 'k_order_rounds' not in names and b[0] - a[-1] > 150:
         table('end-to-end step (16 chunks; appends two chunks ahead)', a[-1] + 1, b[0])
         break
 open(sys.argv[2], 'w').write('\n'.join(out))
