@@ -304,13 +304,14 @@ struct OrderParams {
     int plan_stride;
 };
 
-// Plan: for each new consensus round (ascending, sequential because the "not yet
-// ordered" frontier lastord[] carries over), the famous witnesses f_w, the whitening
+// Plan: for each new consensus round the famous witnesses f_w, the whitening
 // XOR (swirld.py:284-285) and, per member chain c, the range of events this round
 // orders.  On a fork-free graph the reference's BFS over tbd (swirld.py:288-289) reaches
 // exactly the not-yet-ordered events x with x <= max_{w in f_w & tbd} row(w)[c], and
 // "received" (swirld.py:291-293) is monotone along the chain, so the newly ordered
-// events of chain c are (lastord[c], min(reach, received-threshold)].
+// events of chain c are (lastord[c], min(reach, received-threshold)].  Only the frontier lastord[]
+// carries over from round to round: everything else is computed for all rounds at once (A), a
+// 64-thread pass walks the rounds in ascending order (B), the events are listed in parallel (C).
 #define PLAN(k) (P.plan + (size_t)(k) * P.plan_stride)
 
 // A: everything about a consensus round that does not depend on what earlier rounds ordered -- one CTA
