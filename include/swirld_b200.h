@@ -35,7 +35,7 @@ extern "C" {
 #define SW_E_FORK       -7   /* self-parent is not the creator's latest event (fork; swirld.py:110-112 TODO) */
 #define SW_E_UNSUPPORTED -8  /* e.g. M above the compiled kernels' limit */
 
-#define SW_MAX_MEMBERS  64   /* this build: one 64-bit member mask per event */
+#define SW_MAX_MEMBERS  1024 /* member sets are ceil(M/32)-word masks; above 64 members the swirld_wide.cuh kernels run */
 
 typedef struct sw_engine sw_engine;
 
@@ -120,10 +120,19 @@ int sw_flush_l2(sw_engine *e, int64_t bytes);
 int sw_event_record(sw_engine *e, int slot);
 int sw_event_elapsed_ms(sw_engine *e, int slot_a, int slot_b, double *ms_out);
 
-/* Profiling aid: 16 cycle counters of the level walker (compute role [0..7]: process,
- * level-barrier, batch-barrier cycles, events, levels, batches; prepare role [8..15]:
- * stream, prepare, cp.async-wait, batch-barrier cycles). */
+/* Profiling aid: 16 cycle counters of k_rounds_batch (tools/rounds_cycles.py). */
 int sw_debug_counters(sw_engine *e, int64_t *out16, int clear);
+
+/* ---- several GPUs of one box (one process per GPU), M > 64: ONE hashgraph, the P_r tests of every round step of
+ * sw_divide_rounds sharded by member chain over the ranks; every rank writes its chains' first hits straight into
+ * every peer's exchange buffer over NVLink (P2P stores + a system-scope flag) from inside the round kernel -- no
+ * collective library call on the data path, identical state and results on every rank.  (The reference has no
+ * counterpart: it is single-process, swirld.py:331-345.)  sw_peer_handle: the 64-byte CUDA IPC handle of this
+ * engine's exchange buffer; exchange the handles out of band (torch.distributed.all_gather_object), then
+ * sw_peer_connect(rank, nranks <= 8, handles[nranks][64]) before the first sw_divide_rounds.  Every rank must then
+ * make the same sw_append / sw_divide_rounds calls. */
+int sw_peer_handle(sw_engine *e, void *handle_out64);
+int sw_peer_connect(sw_engine *e, int rank, int nranks, const void *handles);
 
 int sw_version(void);
 

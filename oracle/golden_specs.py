@@ -33,6 +33,13 @@ SPECS = {
     # config 2 of BASELINE.json in full, config 3 as a prefix (same K as the bench)
     "g1_m16_n100000_s1_k4096": ("gossip", dict(M=16, N=100000, seed=1), 4096, None),
     "g1_m64_n131072_s1_k65536": ("gossip", dict(M=64, N=131072, seed=1), 65536, None),
+    # beyond 64 members (multi-word member masks): prefixes of BASELINE.json's configs 4 and 5 and mid sizes
+    "g1_m96_n20000_s3_k3000": ("gossip", dict(M=96, N=20000, seed=3), 3000, None),
+    "g1_m80_n8000_s4_k999_stake": ("gossip", dict(M=80, N=8000, seed=4), 999, [1 + (i % 3 == 0) for i in range(80)]),
+    "g2_m128_n40000_s2_k8192": ("adversarial", dict(M=128, N=40000, seed=2, p_cross=0.02, p_stale=0.3), 8192, None),
+    "g3_m128_n12000_s1_k2048": ("tick", dict(M=128, N=12000, seed=1), 2048, None),
+    "g1_m256_n60000_s1_k16384": ("gossip", dict(M=256, N=60000, seed=1), 16384, None),
+    "g1_m1024_n20000_s1_k8192": ("gossip", dict(M=1024, N=20000, seed=1), 8192, None),
 }
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),

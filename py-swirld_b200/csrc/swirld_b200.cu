@@ -1,13 +1,12 @@
 // swirld_b200.cu -- host side of libswirld_b200.so: the C ABI of include/swirld_b200.h
-// over the kernels in swirld_kernels.cuh.  No torch, no CPU compute path: every
+// over the kernels in swirld_*.cuh.  No torch, no CPU compute path: every
 // consensus result is produced by a kernel; the host only validates the graph shape
 // on append (what Node.is_valid_event checks, swirld.py:104-108), keeps the
 // creator/height/chain-position mirrors it needs for that, and moves bytes.
 #include "swirld_kernels.cuh"
-#include "swirld_divide.cuh"
-#include "swirld_levels.cuh"
 #include "swirld_cansee.cuh"
 #include "swirld_rounds.cuh"
+#include "swirld_wide.cuh"
 
 #include <cstdlib>
 #include "../../include/swirld_b200.h"
@@ -29,37 +28,52 @@ struct TimedSpan { cudaEvent_t a, b; int cat; };
 
 struct sw_engine {
     int M = 0, NC = 1, cap = 0, C = 6, device = 0, Rcap = 0;
+    int NJ = 1;                   // words per member set on the wide path: next power of two >= ceil(M/32)
+    int MS = 64;                  // per-round array stride of find_order (64, or M on the wide path)
+    int MP = 64;                  // max(M, 64): size of the per-member scratch arrays
+    bool wide = false;            // swirld_wide.cuh kernels (M > 64, or SW_FORCE_WIDE=1)
     bool unit = true;
     i64 tot = 0;
     std::vector<i64> h_stake;
     // host mirrors for validation / views
     std::vector<int32_t> h_creator, h_head, h_count;
     int32_t *h_height = nullptr, *h_seq = nullptr;   // pinned, cap entries: sources of asynchronous copies
+    uint8_t *h_stale = nullptr;                      // pinned: the other-parent is not its member's latest event
     cudaStream_t copy_stream = nullptr;              // sw_append's copies run beside the kernels of earlier chunks
     struct PendingAppend { int base; cudaEvent_t done; };
     std::vector<PendingAppend> appends;              // copies (+ eager can_see scans) the compute stream has not waited for yet
+    cudaEvent_t scan_ev = nullptr;                   // last can_see scan issued on the compute stream
+    bool scan_ev_set = false;
     int n_events = 0, n_divided = 0, n_tx = 0;
     // device columns
     int32_t *d_p0 = nullptr, *d_p1 = nullptr, *d_creator = nullptr, *d_seq = nullptr, *d_height = nullptr;
-    int32_t *d_hist = nullptr, *d_cursor = nullptr, *d_order = nullptr, *d_gpos = nullptr, *d_lvl_start = nullptr;
-    GDesc *d_gdesc = nullptr;
+    uint8_t *d_stale = nullptr;
     long long *d_dbg = nullptr;
-    unsigned rb_epoch = 0;        // launches of k_rounds_batch (mask-cache key)
-    int divide_impl = 5;          // 5 = round-batch on the whole GPU (default), 4 = level walker, 3 = per-event flags
+    unsigned rb_epoch = 0;        // launches of the round kernel (mask-cache key)
     int n_sm = 0;
     int32_t *d_Wf = nullptr, *d_cev = nullptr, *d_rbmeta = nullptr, *d_rbtot = nullptr, *d_gchain = nullptr;   // round-batch state
     ulonglong2 *d_sc = nullptr;
     uint8_t *d_res = nullptr;
-    int cansee_scan = 0;          // 1 = can_see by the blocked scan k_cs_* (SW_CANSEE_IMPL=scan), 0 = fused into the walker
-    int n_rowed = 0;              // events whose can_see row is complete (cansee_scan)
-    uint8_t *d_exported = nullptr;
-    int32_t *d_exp_list = nullptr, *d_exp_m = nullptr, *d_exp_cnt = nullptr, *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_carry = nullptr;
+    int n_rowed = 0;              // events whose can_see row is complete
+    // can_see scan scratch (swirld_cansee.cuh)
+    int4 *d_cs_meta = nullptr;
+    uint8_t *d_cs_wr = nullptr, *d_cs_xb = nullptr;
+    int32_t *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_carry = nullptr, *d_cs_slow = nullptr, *d_cs_slowcnt = nullptr;
+    int cs_min_B = 256;           // smallest block length the scan uses (sizes the per-block scratch)
     double *d_t = nullptr;
     uint8_t *d_sig = nullptr;
     int32_t *d_row = nullptr, *d_round = nullptr;
-    u64 *d_T = nullptr, *d_SM = nullptr;
+    u64 *d_SM = nullptr;
     uint8_t *d_wit = nullptr;
     int8_t *d_famous_ev = nullptr;
+    // wide path
+    unsigned *d_scw = nullptr, *d_SMw = nullptr, *d_Sw = nullptr;
+    u64 *d_sctag = nullptr, *d_hitmin = nullptr;
+    // several GPUs (sw_peer_connect): tests of a round step sharded by chain, first hits exchanged over NVLink
+    int rank = 0, nranks = 1;
+    void *d_xbuf = nullptr;       // [flags: 64 x u32][hits: 8 x 3 x M x u64], IPC-exported
+    void *x_peer[8] = {nullptr};  // the same buffer of every rank (own: d_xbuf)
+    unsigned *d_xstep = nullptr;  // steps published so far (device-resident: the step count of a launch is data dependent)
     // per round
     int32_t *d_W = nullptr, *d_rem = nullptr, *d_newc = nullptr;
     u64 *d_S = nullptr;
@@ -106,6 +120,11 @@ int fail(sw_engine *e, int code, const char *fmt, ...) {
             return fail(e, SW_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_s),   \
                         __FILE__, __LINE__);                                             \
     } while (0)
+
+// call F<NJ>(args) for the engine's word count
+#define SW_NJ(F, ...)                                                                    \
+    (e->NJ == 1 ? F<1>(__VA_ARGS__) : e->NJ == 2 ? F<2>(__VA_ARGS__) : e->NJ == 4 ? F<4>(__VA_ARGS__) \
+     : e->NJ == 8 ? F<8>(__VA_ARGS__) : e->NJ == 16 ? F<16>(__VA_ARGS__) : F<32>(__VA_ARGS__))
 
 template <typename T>
 cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
@@ -157,7 +176,8 @@ int device_error(sw_engine *e) {     // after a sync: did a kernel flag an error
     if (code < 0) {
         const char *what = code == SW_E_CAPACITY ? "round table exhausted"
                          : code == SW_E_INDEX ? "list index out of range (swirld.py:305: a single seer)"
-                         : code == SW_E_KEY ? "KeyError (undecided witness in a consensus round)" : "device error";
+                         : code == SW_E_KEY ? "KeyError (undecided witness in a consensus round)"
+                         : code == SW_E_CUDA ? "a peer GPU did not publish its round step in time (multi-GPU exchange)" : "device error";
         return fail(e, code, "%s", what);
     }
     return 0;
@@ -167,23 +187,29 @@ int reset_state(sw_engine *e, bool keep_events = false) {
     const size_t RM = (size_t)e->Rcap * e->M;
     k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_W, -1, RM);
     CK(cudaMemsetAsync(e->d_famous, 0xff, RM, e->stream));
-    CK(cudaMemsetAsync(e->d_S, 0, RM * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_consensus, 0, e->Rcap, e->stream));
     CK(cudaMemsetAsync(e->d_famous_ev, 0xff, e->cap, e->stream));
     k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_idx, -1, (size_t)e->cap);
-    k_fill_i32<<<1, 64, 0, e->stream>>>(e->d_lastord, -1, (size_t)e->M);
-    k_fill_i32<<<1, 64, 0, e->stream>>>(e->d_cs_carry, -1, (size_t)64);
+    k_fill_i32<<<4, 256, 0, e->stream>>>(e->d_lastord, -1, (size_t)e->MP);
+    k_fill_i32<<<4, 256, 0, e->stream>>>(e->d_cs_carry, -1, (size_t)e->MP);
     k_fill_i32<<<256, 256, 0, e->stream>>>(e->d_Wf, -1, RM);
-    CK(cudaMemsetAsync(e->d_rbtot, 0, sizeof(int32_t) * 64, e->stream));
-    k_fill_i32<<<64, 256, 0, e->stream>>>(e->d_gchain, -1, (size_t)64 * RB_RING);
-    CK(cudaMemsetAsync(e->d_sc, 0, sizeof(ulonglong2) * (size_t)e->cap, e->stream));
+    CK(cudaMemsetAsync(e->d_rbtot, 0, sizeof(int32_t) * e->MP, e->stream));
+    k_fill_i32<<<64, 256, 0, e->stream>>>(e->d_gchain, -1, (size_t)e->MP * RB_RING);
+    if (e->wide) {
+        CK(cudaMemsetAsync(e->d_Sw, 0, RM * e->NJ * sizeof(unsigned), e->stream));
+        CK(cudaMemsetAsync(e->d_sctag, 0, sizeof(u64) * (size_t)e->cap, e->stream));
+    } else {
+        CK(cudaMemsetAsync(e->d_S, 0, RM * sizeof(u64), e->stream));
+        CK(cudaMemsetAsync(e->d_sc, 0, sizeof(ulonglong2) * (size_t)e->cap, e->stream));
+    }
     int32_t sc[SC_COUNT] = {0};
     sc[SC_MAX_ROUND] = -1;
     CK(cudaMemcpyAsync(e->d_scal, sc, sizeof sc, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    e->stats.kernel_launches += 3;
+    e->stats.kernel_launches += 5;
     e->n_divided = e->n_tx = 0;
     e->n_rowed = 0;
+    e->rb_epoch = 0;
     if (!keep_events) {
         e->n_events = 0;
         std::fill(e->h_head.begin(), e->h_head.end(), -1);
@@ -193,98 +219,71 @@ int reset_state(sw_engine *e, bool keep_events = false) {
     return 0;
 }
 
-template <int NC, bool UNIT>
-int launch_divide(sw_engine *e, const DivParams &P) {
-    const size_t smem = sizeof(DivSmem<NC>);
-    CK(cudaFuncSetAttribute(k_divide<NC, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_divide<NC, UNIT><<<1, 1024, smem, e->stream>>>(P);
-    CK(cudaGetLastError());
-    return 0;
-}
-
-template <int NC, bool UNIT, bool ROWS, bool FULL>
-int launch_levels4(sw_engine *e, const Div4Params &Q) {
-    const size_t smem = sizeof(LvSmem<NC, ROWS>);
-    CK(cudaFuncSetAttribute(k_divide_levels<NC, UNIT, ROWS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        cudaEvent_t a = get_event(e), b = get_event(e);
-        cudaEventRecord(a, e->stream);
-        k_divide_levels<NC, UNIT, ROWS, FULL><<<1, LV_THREADS, smem, e->stream>>>(Q);
-        cudaEventRecord(b, e->stream);
-        e->spans.push_back(TimedSpan{a, b, 4});
-    }
-    CK(cudaGetLastError());
-    return 0;
-}
-template <int NC, bool UNIT, bool ROWS>
-int launch_levels(sw_engine *e, const Div4Params &Q) {
-    return e->M == NC * 32 ? launch_levels4<NC, UNIT, ROWS, true>(e, Q) : launch_levels4<NC, UNIT, ROWS, false>(e, Q);
-}
-
-// can_see rows of every appended event that does not have one yet: blocked scan (k_cs_*)
-// `st`: the compute stream (lazily, from sw_divide_rounds) or the copy stream (eagerly, from sw_append:
-// the scan of a new chunk then runs beside the round kernel of the previous one)
-template <int NC>
+// can_see rows of the appended events [n_rowed, upto): the column-tiled blocked scan of swirld_cansee.cuh.
+// `st`: the compute stream (lazily, from sw_divide_rounds) or the copy stream (eagerly, from sw_append: the
+// scan of a new chunk then runs beside the round kernel of the previous one).  The two never overlap: a scan
+// on one stream first waits for the last scan issued on the other (they share the scratch and the carry heads).
 int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     const int first = e->n_rowed, n = upto - e->n_rowed;
     if (n <= 0) return 0;
+    const int M = e->M;
     CsParams C{};
-    C.M = e->M; C.first = first; C.n = n;
-    // block length: the in-block walks are serial in B, the boundary pass in n/B (SW_CS_B overrides)
-    C.B = std::min(n, n >= 200000 ? 4096 : 1024);
-    if (const char *v = getenv("SW_CS_B")) C.B = std::max(64, std::min(n, atoi(v)));
-    C.nb = (n + C.B - 1) / C.B;
-    C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.row = e->d_row;
-    C.exported = e->d_exported; C.exp_list = e->d_exp_list; C.exp_m = e->d_exp_m; C.exp_cnt = e->d_exp_cnt;
-    C.last = e->d_cs_last; C.Qtab = e->d_cs_Q; C.carry = e->d_cs_carry;
-    CK(cudaMemsetAsync(e->d_exported + first, 0, (size_t)n, st));
-    CK(cudaMemsetAsync(e->d_exp_cnt, 0, sizeof(int32_t) * (size_t)C.nb, st));
+    C.M = M; C.first = first; C.n = n;
+    C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.stale = e->d_stale; C.row = e->d_row;
+    C.meta = e->d_cs_meta; C.wr = e->d_cs_wr; C.xb = e->d_cs_xb; C.last = e->d_cs_last; C.Qtab = e->d_cs_Q;
+    C.carry = e->d_cs_carry; C.slow_list = e->d_cs_slow; C.slow_cnt = e->d_cs_slowcnt;
     cudaEvent_t a = get_event(e), b = get_event(e);
+    int small_n = 24;
+    if (const char *v = getenv("SW_CS_SMALL")) small_n = atoi(v);
+    if (n <= small_n) {                                // the reference's own cadence: a handful of events per call
+        cudaEventRecord(a, st);
+        k_cs_small<<<1, std::min(1024, (M + 31) / 32 * 32), 0, st>>>(C);
+        cudaEventRecord(b, st);
+        e->spans.push_back(TimedSpan{a, b, 3});
+        CK(cudaGetLastError());
+        e->stats.kernel_launches += 1;
+        e->n_rowed = upto;
+        return 0;
+    }
+    // block length: >= 16 events per member and block, so that every member's last event of a block sees every
+    // block-start head (then the boundary check passes and nothing is left for the serial pass); SW_CS_B overrides
+    int B = std::max(e->cs_min_B, std::min(16 * M, 1 << 15));
+    if (const char *v = getenv("SW_CS_B")) B = std::max(e->cs_min_B, atoi(v));
+    B = (B + 3) & ~3;
+    C.B = B;
+    C.first_al = first & ~3;
+    C.nb = (first + n <= C.first_al + B) ? 1 : 1 + (first + n - (C.first_al + B) + B - 1) / B;
+    const int ntiles = (M + CS_CT - 1) / CS_CT;
+    const size_t smem = (size_t)M * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
+    const int pblocks = std::max(1, std::min(8 * e->n_sm, (n + 255) / 256));
+    k_fill_i32<<<std::max(1, std::min(256, (int)(((size_t)C.nb * M + 255) / 256))), 256, 0, st>>>(e->d_cs_last, -1, (size_t)C.nb * M);
+    if (C.nb > 1) {
+        CK(cudaMemsetAsync(e->d_cs_wr + first, 0, (size_t)n, st));
+        CK(cudaMemsetAsync(e->d_cs_xb + first, 0, (size_t)n, st));
+        CK(cudaMemsetAsync(e->d_cs_slowcnt, 0, sizeof(int32_t) * ((size_t)C.nb + 1), st));
+    }
     cudaEventRecord(a, st);
-    k_cs_local<NC, 1><<<C.nb, NC * 32, 0, st>>>(C);
-    k_cs_collect<<<std::max(1, std::min(296, (n + 255) / 256)), 256, 0, st>>>(C);
-    k_cs_boundary<NC><<<1, 1024, 0, st>>>(C);
-    k_cs_local<NC, 2><<<C.nb, NC * 32, 0, st>>>(C);
+    k_cs_prep<<<pblocks, 256, 0, st>>>(C);
+    if (C.nb > 1) k_cs_pass<1><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+    k_cs_heads<<<(M + 127) / 128, 128, 0, st>>>(C);
+    if (C.nb > 1) {
+        k_cs_check<<<pblocks, 256, 0, st>>>(C);
+        k_cs_slow<<<1, CS_SLOW_WARPS * 32, (size_t)CS_SLOW_WARPS * M * sizeof(int), st>>>(C);
+    }
+    k_cs_pass<2><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
     cudaEventRecord(b, st);
     e->spans.push_back(TimedSpan{a, b, 3});
     CK(cudaGetLastError());
-    e->stats.kernel_launches += 4;
+    e->stats.kernel_launches += C.nb > 1 ? 7 : 4;
     e->n_rowed = upto;
     return 0;
 }
 
-// counting sort of the chunk by height, then the level-scheduled walk
-int divide_levels(sw_engine *e, const DivParams &P) {
-    int hmin = e->h_height[P.first], hmax = hmin;
-    for (int i = P.first; i < P.first + P.n; i++) { hmin = std::min(hmin, e->h_height[i]); hmax = std::max(hmax, e->h_height[i]); }
-    LvlParams L{};
-    L.first = P.first; L.n = P.n; L.hmin = hmin; L.nbins = hmax - hmin + 1;
-    L.height = e->d_height; L.p0 = e->d_p0; L.p1 = e->d_p1; L.creator = e->d_creator;
-    L.hist = e->d_hist; L.cursor = e->d_cursor; L.order = e->d_order; L.gpos = e->d_gpos;
-    L.lvl_start = e->d_lvl_start; L.scal = e->d_scal; L.gdesc = e->d_gdesc;
-    CK(cudaMemsetAsync(e->d_hist, 0, sizeof(int32_t) * (size_t)L.nbins, e->stream));
-    const int blocks = std::max(1, std::min(296, (P.n + 255) / 256));
-    k_lvl_hist<<<blocks, 256, 0, e->stream>>>(L);
-    k_lvl_scan<<<1, 1024, 0, e->stream>>>(L);
-    k_lvl_scatter<<<blocks, 256, 0, e->stream>>>(L);
-    k_lvl_desc<<<blocks, 256, 0, e->stream>>>(L);
-    CK(cudaGetLastError());
-    Div4Params Q{};
-    Q.d = P; Q.gdesc = e->d_gdesc; Q.lvl_start = e->d_lvl_start;
-    e->stats.kernel_launches += 4;
-    if (e->cansee_scan) {
-        if (e->NC == 1) return e->unit ? launch_levels<1, true, false>(e, Q) : launch_levels<1, false, false>(e, Q);
-        return e->unit ? launch_levels<2, true, false>(e, Q) : launch_levels<2, false, false>(e, Q);
-    }
-    if (e->NC == 1) return e->unit ? launch_levels<1, true, true>(e, Q) : launch_levels<1, false, true>(e, Q);
-    return e->unit ? launch_levels<2, true, true>(e, Q) : launch_levels<2, false, true>(e, Q);
-}
-
-// rounds of the chunk by the cooperative round-batch kernel (swirld_rounds.cuh)
+// rounds of the chunk by the cooperative round-batch kernel (swirld_rounds.cuh), M <= 64
 template <int NC, bool UNIT>
-int divide_round_batch(sw_engine *e, const DivParams &D) {
+int divide_round_batch(sw_engine *e, int first, int n) {
     RbParams R{};
-    R.M = e->M; R.first = D.first; R.n = D.n; R.Rcap = e->Rcap;
+    R.M = e->M; R.first = first; R.n = n; R.Rcap = e->Rcap;
     // a few SMs stay free for the can_see scan of the next chunk, which runs beside this kernel (SW_RB_FREE_SMS)
     int free_sms = 16;
     if (const char *v = getenv("SW_RB_FREE_SMS")) free_sms = std::max(0, atoi(v));
@@ -298,12 +297,12 @@ int divide_round_batch(sw_engine *e, const DivParams &D) {
     R.Wf = e->d_Wf; R.sc = e->d_sc; R.cev = e->d_cev;
     R.ccnt = e->d_rbmeta; R.cmin = e->d_rbmeta + 64; R.coff = e->d_rbmeta + 128; R.bar = reinterpret_cast<unsigned *>(e->d_rbmeta + 224);
     R.ctot = e->d_rbtot; R.gchain = e->d_gchain;
-    R.res = e->d_res; R.stake = e->d_stake; R.tot2 = D.tot2; R.scal = e->d_scal;
+    R.res = e->d_res; R.stake = e->d_stake; R.tot2 = 2 * e->tot; R.scal = e->d_scal;
     R.wit = e->d_wit; R.W = e->d_W; R.SM = e->d_SM; R.dbg = e->d_dbg;
     R.wlist = e->d_cev + e->cap; R.wcnt = e->d_rbmeta + 225;
     CK(cudaMemsetAsync(R.ccnt, 0, sizeof(int32_t) * 64, e->stream));
     CK(cudaMemsetAsync(R.cmin, 0x7f, sizeof(int32_t) * 64, e->stream));
-    const int blocks = std::max(1, std::min(296, (D.n + 255) / 256));
+    const int blocks = std::max(1, std::min(296, (n + 255) / 256));
     k_rb_count<<<blocks, 256, 0, e->stream>>>(R);
     k_rb_offsets<<<1, 32, 0, e->stream>>>(R);
     k_rb_scatter<<<blocks, 256, 0, e->stream>>>(R);
@@ -318,9 +317,88 @@ int divide_round_batch(sw_engine *e, const DivParams &D) {
     }
     k_rb_tail<<<blocks, 256, 0, e->stream>>>(R);
     k_rb_witness<<<blocks, 256, 0, e->stream>>>(R);
-    k_rb_seenmask<NC><<<(D.n + 7) / 8, 256, 0, e->stream>>>(R);
+    k_rb_seenmask<NC><<<(n + 7) / 8, 256, 0, e->stream>>>(R);
     CK(cudaGetLastError());
-    e->stats.kernel_launches += 7;
+    // decide_fame's strongly-seen sets of the chunk's witnesses
+    StrongParams Q{};
+    Q.M = e->M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
+    Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
+    Q.coin = e->d_coin; Q.sig = e->d_sig; Q.unit = e->unit ? 1 : 0;
+    Q.list = R.wlist; Q.list_n = R.wcnt;
+    const int sblocks = std::max(1, std::min((n + 7) / 8, 4 * e->n_sm));
+    k_strong<NC><<<sblocks, 256, 0, e->stream>>>(Q);
+    CK(cudaGetLastError());
+    e->stats.kernel_launches += 8;
+    return 0;
+}
+
+size_t rounds_wide_smem(int M) { return (size_t)(2 * M + 14 * M + 1 + 32 + (RW_THREADS / 32) * M + 1) * sizeof(int); }
+
+// rounds of the chunk for any member count (swirld_wide.cuh)
+template <int NJ>
+int divide_rounds_wide(sw_engine *e, int first, int n) {
+    const int M = e->M;
+    RwParams R{};
+    R.M = M; R.first = first; R.n = n; R.Rcap = e->Rcap;
+    const int grid = e->n_sm;
+    const int nw = grid * (RW_THREADS / 32);
+    const int nown = (M + e->nranks - 1) / e->nranks;
+    R.L = std::max(2, std::min(RW_LMAX, 2 * nw / std::max(1, nown)));
+    if (const char *v = getenv("SW_RW_L")) R.L = std::max(1, std::min(RW_LMAX, atoi(v)));
+    R.epoch = ++e->rb_epoch;
+    R.row = e->d_row; R.p0 = e->d_p0; R.creator = e->d_creator; R.seq = e->d_seq; R.round = e->d_round;
+    R.Wf = e->d_Wf; R.scw = e->d_scw; R.sctag = e->d_sctag; R.cev = e->d_cev;
+    R.ccnt = e->d_rbmeta; R.cmin = e->d_rbmeta + M; R.coff = e->d_rbmeta + 2 * M; R.bar = reinterpret_cast<unsigned *>(e->d_rbmeta + 3 * M + 8);
+    int32_t *wcnt = e->d_rbmeta + 3 * M + 9, *wlist = e->d_cev + e->cap;
+    R.ctot = e->d_rbtot; R.gchain = e->d_gchain; R.hitmin = e->d_hitmin;
+    R.stake = e->d_stake; R.tot2 = 2 * e->tot; R.unit = e->unit ? 1 : 0; R.scal = e->d_scal; R.dbg = e->d_dbg;
+    R.rank = e->rank; R.nranks = e->nranks; R.xstep = e->d_xstep;
+    for (int p = 0; p < e->nranks && p < 8; p++) {
+        R.xflag[p] = reinterpret_cast<unsigned *>(e->x_peer[p]);
+        R.xhit[p] = reinterpret_cast<u64 *>(reinterpret_cast<char *>(e->x_peer[p]) + 256);
+    }
+    CK(cudaMemsetAsync(R.ccnt, 0, sizeof(int32_t) * M, e->stream));
+    CK(cudaMemsetAsync(R.cmin, 0x7f, sizeof(int32_t) * M, e->stream));
+    const int blocks = std::max(1, std::min(2 * e->n_sm, (n + 255) / 256));
+    k_rw_count<<<blocks, 256, 0, e->stream>>>(R);
+    k_rw_offsets<<<1, 1024, 0, e->stream>>>(R, wcnt);
+    k_rw_scatter<<<blocks, 256, 0, e->stream>>>(R);
+    CK(cudaGetLastError());
+    const size_t smem = rounds_wide_smem(M);
+    CK(cudaFuncSetAttribute(k_rounds_wide<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {(void *)&R};
+    {
+        cudaEvent_t a = get_event(e), b = get_event(e);
+        cudaEventRecord(a, e->stream);
+        CK(cudaLaunchCooperativeKernel((void *)k_rounds_wide<NJ>, dim3(grid), dim3(RW_THREADS), args, smem, e->stream));
+        cudaEventRecord(b, e->stream);
+        e->spans.push_back(TimedSpan{a, b, 4});
+    }
+    RbParams T{};                                      // the finish kernels shared with the M <= 64 path
+    T.M = M; T.first = first; T.n = n; T.Rcap = e->Rcap; T.p0 = e->d_p0; T.creator = e->d_creator; T.seq = e->d_seq;
+    T.round = e->d_round; T.ctot = e->d_rbtot; T.gchain = e->d_gchain; T.wit = e->d_wit; T.W = e->d_W;
+    T.wlist = wlist; T.wcnt = wcnt;
+    k_rb_tail<<<blocks, 256, 0, e->stream>>>(T);
+    k_rb_witness<<<blocks, 256, 0, e->stream>>>(T);
+    k_w_seenmask<NJ><<<std::max(1, std::min(8 * e->n_sm, (n + 7) / 8)), 256, 0, e->stream>>>(M, first, n, e->Rcap, e->d_row, e->d_round, e->d_W, e->d_SMw);
+    CK(cudaGetLastError());
+    StrongParams Q{};
+    Q.M = M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
+    Q.round = e->d_round; Q.wit = e->d_wit; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
+    Q.coin = e->d_coin; Q.sig = e->d_sig; Q.unit = e->unit ? 1 : 0; Q.list = wlist; Q.list_n = wcnt;
+    Q.SMw = e->d_SMw; Q.Sw = e->d_Sw;
+    const size_t ssm = (size_t)(2 * M + 8 * M) * sizeof(int);
+    CK(cudaFuncSetAttribute(k_w_strong<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+    k_w_strong<NJ><<<std::max(1, std::min(4 * e->n_sm, (n + 7) / 8)), 256, ssm, e->stream>>>(Q);
+    CK(cudaGetLastError());
+    e->stats.kernel_launches += 8;
+    return 0;
+}
+
+template <int NJ>
+int fame_rounds_wide(sw_engine *e, const FameParams &P) {
+    const size_t smem = (size_t)(32 * NJ + 64) * sizeof(int) + (size_t)(32 + e->M) * sizeof(i64);
+    k_w_fame_rounds<NJ><<<2 * e->n_sm, 1024, smem, e->stream>>>(P);
     return 0;
 }
 
@@ -328,7 +406,7 @@ int divide_round_batch(sw_engine *e, const DivParams &D) {
 
 extern "C" {
 
-int sw_version(void) { return 100; }
+int sw_version(void) { return 200; }
 
 const char *sw_last_error(const sw_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
@@ -345,6 +423,12 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
     if (device < 0 || device >= ndev) return fail(e, SW_E_ARG, "device %d out of range (%d devices)", device, ndev);
     e = new sw_engine();
     e->M = M; e->NC = (M + 31) / 32; e->cap = capacity_events; e->C = coin_period; e->device = device;
+    e->wide = M > 64;
+    if (const char *v = getenv("SW_FORCE_WIDE")) if (atoi(v)) e->wide = true;
+    e->NJ = 1;
+    while (e->NJ * 32 < M) e->NJ *= 2;
+    e->MS = e->wide ? M : 64;
+    e->MP = std::max(M, 64);
     e->h_stake.resize(M);
     for (int c = 0; c < M; c++) {
         e->h_stake[c] = stake ? stake[c] : 1;
@@ -356,10 +440,6 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
     i64 per = std::min<i64>(M, (2 * e->tot) / 3 + 1);
     if (per < 1) per = 1;
     e->Rcap = (int)std::min<i64>((i64)e->cap + 2, (i64)e->cap / per + 16);
-    if (const char *impl = getenv("SW_DIVIDE_IMPL")) { int v = atoi(impl); e->divide_impl = (v == 3 || v == 4) ? v : 5; }
-    if (const char *impl = getenv("SW_CANSEE_IMPL")) e->cansee_scan = strcmp(impl, "scan") == 0 ? 1 : 0;
-    if (e->divide_impl == 3) e->cansee_scan = 0;
-    if (e->divide_impl == 5) e->cansee_scan = 1;     // the round-batch kernel reads finished can_see rows
     e->h_head.assign(M, -1);
     e->h_count.assign(M, 0);
     e->h_creator.reserve(e->cap);
@@ -367,34 +447,52 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        const size_t cap = e->cap, RM = (size_t)e->Rcap * M;
+        CK(cudaEventCreateWithFlags(&e->scan_ev, cudaEventDisableTiming));
+        const size_t cap = e->cap, RM = (size_t)e->Rcap * M, MP = e->MP;
         CK(cudaMallocHost((void **)&e->h_height, sizeof(int32_t) * cap));
         CK(cudaMallocHost((void **)&e->h_seq, sizeof(int32_t) * cap));
+        CK(cudaMallocHost((void **)&e->h_stale, cap));
         CK(dalloc(&e->d_p0, cap)); CK(dalloc(&e->d_p1, cap)); CK(dalloc(&e->d_creator, cap)); CK(dalloc(&e->d_seq, cap));
-        CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64)); CK(dalloc(&e->d_height, cap));
-        CK(dalloc(&e->d_hist, cap + 2)); CK(dalloc(&e->d_cursor, cap + 2)); CK(dalloc(&e->d_order, cap));
-        CK(dalloc(&e->d_gpos, cap)); CK(dalloc(&e->d_lvl_start, cap + 2)); CK(dalloc(&e->d_gdesc, cap));
-        CK(dalloc(&e->d_exported, cap)); CK(dalloc(&e->d_exp_list, cap + 8192)); CK(dalloc(&e->d_exp_m, cap + 8192)); CK(dalloc(&e->d_exp_cnt, cap / 64 + 4));
-        CK(dalloc(&e->d_cs_last, (cap / 64 + 4) * (size_t)M)); CK(dalloc(&e->d_cs_Q, (cap / 64 + 5) * (size_t)M));
-        CK(dalloc(&e->d_cs_carry, (size_t)64));
-        CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, 2 * cap)); /* + the witness list of the current chunk */ CK(dalloc(&e->d_rbmeta, (size_t)256));
-        CK(dalloc(&e->d_sc, cap)); CK(dalloc(&e->d_res, (size_t)2 * 64 * RB_LMAX));
-        CK(dalloc(&e->d_rbtot, (size_t)64)); CK(dalloc(&e->d_gchain, (size_t)64 * RB_RING));
+        CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64)); CK(dalloc(&e->d_height, cap)); CK(dalloc(&e->d_stale, cap));
+        // can_see scan scratch: per-event meta / flags / slow list, per-block tables (blocks are >= cs_min_B events)
+        e->cs_min_B = std::max(256, std::min(16 * M, 1 << 15));
+        if (const char *v = getenv("SW_CS_B")) e->cs_min_B = std::max(64, std::min(e->cs_min_B, atoi(v)));
+        const size_t nbmax = cap / e->cs_min_B + 3;
+        CK(dalloc(&e->d_cs_meta, cap)); CK(dalloc(&e->d_cs_wr, cap)); CK(dalloc(&e->d_cs_xb, cap)); CK(dalloc(&e->d_cs_slow, cap + 4));
+        CK(dalloc(&e->d_cs_last, nbmax * M)); CK(dalloc(&e->d_cs_Q, (nbmax + 1) * M)); CK(dalloc(&e->d_cs_slowcnt, nbmax + 1));
+        CK(dalloc(&e->d_cs_carry, MP));
+        CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, 2 * cap)); /* + the witness list of the current chunk */
+        CK(dalloc(&e->d_rbmeta, std::max<size_t>(256, 3 * MP + 64)));
+        CK(dalloc(&e->d_rbtot, MP)); CK(dalloc(&e->d_gchain, MP * RB_RING));
         CK(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
         CK(dalloc(&e->d_dbg, (size_t)40)); CK(cudaMemsetAsync(e->d_dbg, 0, sizeof(long long) * 40, e->stream));
-        CK(dalloc(&e->d_row, cap * M)); CK(dalloc(&e->d_SM, cap));
-        if (e->divide_impl != 5) CK(dalloc(&e->d_T, cap * M));           // strongly-sees matrices: level walker only
+        CK(dalloc(&e->d_row, cap * M));
+        if (e->wide) {
+            CK(dalloc(&e->d_scw, cap * e->NJ)); CK(dalloc(&e->d_sctag, cap)); CK(dalloc(&e->d_SMw, cap * e->NJ));
+            CK(dalloc(&e->d_Sw, RM * e->NJ)); CK(dalloc(&e->d_hitmin, (size_t)3 * M));
+            CK(cudaMalloc(&e->d_xbuf, 256 + (size_t)8 * 3 * M * sizeof(u64)));
+            CK(cudaMemsetAsync(e->d_xbuf, 0, 256 + (size_t)8 * 3 * M * sizeof(u64), e->stream));
+            CK(dalloc(&e->d_xstep, (size_t)1)); CK(cudaMemsetAsync(e->d_xstep, 0, sizeof(unsigned), e->stream));
+            e->x_peer[0] = e->d_xbuf;
+        } else {
+            CK(dalloc(&e->d_sc, cap)); CK(dalloc(&e->d_res, (size_t)2 * 64 * RB_LMAX));
+            CK(dalloc(&e->d_SM, cap)); CK(dalloc(&e->d_S, RM));
+        }
         CK(dalloc(&e->d_round, cap)); CK(dalloc(&e->d_wit, cap)); CK(dalloc(&e->d_famous_ev, cap));
-        CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_S, RM)); CK(dalloc(&e->d_famous, RM));
+        CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_famous, RM));
         CK(dalloc(&e->d_consensus, (size_t)e->Rcap)); CK(dalloc(&e->d_done, (size_t)e->Rcap)); CK(dalloc(&e->d_coin, RM));
         CK(dalloc(&e->d_rem, (size_t)e->Rcap)); CK(dalloc(&e->d_newc, (size_t)e->Rcap));
         CK(dalloc(&e->d_stake, (size_t)M)); CK(dalloc(&e->d_scal, (size_t)SC_COUNT));
-        CK(dalloc(&e->d_lastord, (size_t)64)); CK(dalloc(&e->d_tx, cap)); CK(dalloc(&e->d_idx, cap));
+        CK(dalloc(&e->d_lastord, MP)); CK(dalloc(&e->d_tx, cap)); CK(dalloc(&e->d_idx, cap));
         CK(dalloc(&e->d_batch_ev, cap)); CK(dalloc(&e->d_batch_seg, cap)); CK(dalloc(&e->d_perm, 2 * cap));
         CK(dalloc(&e->d_ts, cap)); CK(dalloc(&e->d_key, cap * 8));
         CK(cudaMallocHost((void **)&e->h_scal, sizeof(int32_t) * SC_COUNT));
         CK(cudaMallocHost((void **)&e->h_newc, sizeof(int32_t) * e->Rcap));
         CK(cudaMemcpyAsync(e->d_stake, e->h_stake.data(), sizeof(i64) * M, cudaMemcpyHostToDevice, e->stream));
+        // kernels that need more than the default 48 KB of dynamic shared memory
+        const size_t cs_smem = (size_t)M * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
+        CK(cudaFuncSetAttribute(k_cs_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         return reset_state(e);
     }();
     if (rc < 0) { g_create_error = e->err; sw_destroy(e); return rc; }
@@ -407,11 +505,16 @@ void sw_destroy(sw_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) { wait_appends(e, -1); cudaStreamSynchronize(e->stream); }
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     fold_spans(e);
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
-    void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_carry, e->d_exported, e->d_exp_list, e->d_exp_m, e->d_exp_cnt, e->d_coin, e->d_dbg, e->d_height, e->d_hist, e->d_cursor, e->d_order, e->d_gpos, e->d_lvl_start, e->d_gdesc,
-                    e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_T, e->d_SM,
+    if (e->scan_ev) cudaEventDestroy(e->scan_ev);
+    for (int p = 0; p < 8; p++) if (e->x_peer[p] && e->x_peer[p] != e->d_xbuf) cudaIpcCloseMemHandle(e->x_peer[p]);
+    void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_carry,
+                    e->d_cs_meta, e->d_cs_wr, e->d_cs_xb, e->d_cs_slow, e->d_cs_slowcnt, e->d_stale, e->d_coin, e->d_dbg, e->d_height,
+                    e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_SM,
+                    e->d_scw, e->d_sctag, e->d_SMw, e->d_Sw, e->d_hitmin, e->d_xbuf, e->d_xstep,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
                     e->d_batch_ev, e->d_batch_seg, e->d_perm, e->d_ts, e->d_key, e->d_seg_start, e->d_seg_fw,
@@ -421,6 +524,7 @@ void sw_destroy(sw_engine *e) {
     if (e->h_newc) cudaFreeHost(e->h_newc);
     if (e->h_height) cudaFreeHost(e->h_height);
     if (e->h_seq) cudaFreeHost(e->h_seq);
+    if (e->h_stale) cudaFreeHost(e->h_stale);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -480,6 +584,7 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
     for (int j = 0; j < n && rc == SW_OK; j++) {
         const int i = base + j, c = creator[j], a = p0[j], b = p1[j];
         if (c < 0 || c >= e->M) { rc = fail(e, SW_E_ARG, "event %d: creator %d out of range", i, c); break; }
+        e->h_stale[i] = 0;
         if (a < 0 && b < 0) {
             if (e->h_head[c] >= 0) { rc = fail(e, SW_E_FORK, "event %d: second root of member %d", i, c); break; }
             e->h_height[i] = 0;                                          // swirld.py:117-118
@@ -489,6 +594,7 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
             if (e->h_creator[b] == c) { rc = fail(e, SW_E_PARENT, "event %d: other-parent %d has the same creator", i, b); break; }
             if (e->h_head[c] != a) { rc = fail(e, SW_E_FORK, "event %d: self-parent %d is not member %d's latest event (fork)", i, a, c); break; }
             e->h_height[i] = std::max(e->h_height[a], e->h_height[b]) + 1;   // swirld.py:120
+            e->h_stale[i] = e->h_head[e->h_creator[b]] != b;             // "near fork": an older event of the peer
         }
         e->h_creator[i] = c;
         e->h_head[c] = i;
@@ -509,13 +615,15 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
     CK(cudaMemcpyAsync(e->d_sig + (size_t)base * 64, sig, (size_t)64 * n, cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync(e->d_seq + base, e->h_seq + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync(e->d_height + base, e->h_height + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(e->d_stale + base, e->h_stale + base, (size_t)n, cudaMemcpyHostToDevice, cs));
     // rows are up to date and the batch is big: scan it now, beside the kernels of the previous chunk
-    const bool eager = e->cansee_scan && e->n_rowed == base && n >= 4096;
-    e->stats.h2d_bytes += (i64)n * (5 * 4 + 8 + 64);
+    const bool eager = e->n_rowed == base && n >= 4096;
+    e->stats.h2d_bytes += (i64)n * (5 * 4 + 1 + 8 + 64);
     e->stats.events += n;
     e->n_events += n;
     if (eager) {
-        int rc2 = e->NC == 1 ? cansee_scan<1>(e, cs, e->n_events) : cansee_scan<2>(e, cs, e->n_events);
+        if (e->scan_ev_set) CK(cudaStreamWaitEvent(cs, e->scan_ev, 0));     // never beside a scan on the compute stream
+        int rc2 = cansee_scan(e, cs, e->n_events);
         if (rc2 < 0) return rc2;
     }
     // the compute stream waits for this batch only when a call first touches it (wait_appends)
@@ -531,44 +639,23 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     if (first != e->n_divided) return fail(e, SW_E_ARG, "divide_rounds: first=%d but %d events are divided (events must arrive in order)", first, e->n_divided);
     if (first + n > e->n_events) return fail(e, SW_E_KEY, "divide_rounds: events [%d,%d) not appended", first, first + n);
     CK(cudaSetDevice(e->device));
-    if (wait_appends(e, first + n) < 0) return SW_E_CUDA;
-    DivParams P{};
-    P.M = e->M; P.first = first; P.n = n; P.Rcap = e->Rcap;
-    P.p0 = e->d_p0; P.p1 = e->d_p1; P.creator = e->d_creator;
-    P.row = e->d_row; P.T = e->d_T; P.SM = e->d_SM; P.round = e->d_round; P.wit = e->d_wit; P.W = e->d_W;
-    P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.scal = e->d_scal; P.dbg = e->d_dbg;
-    StrongParams Q{};
-    Q.M = e->M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
-    Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
-    Q.coin = e->d_coin; Q.sig = e->d_sig; Q.unit = e->unit ? 1 : 0;
-    if (e->cansee_scan && first + n > e->n_rowed) {
-        // rows are behind (small appends, or after sw_rewind): scan everything appended so far, here.
-        // (Scanning only [n_rowed, first+n) here and the rest on the copy stream beside the round kernels was
-        // measured: 1% faster on average at C3, but with a visible run-to-run spread.)
-        int rc = e->NC == 1 ? cansee_scan<1>(e, e->stream, e->n_events) : cansee_scan<2>(e, e->stream, e->n_events);
+    if (first + n > e->n_rowed) {
+        // rows are behind (small appends, or after sw_rewind): scan everything appended so far, here -- after the
+        // copies of EVERY appended batch (the scan reads the columns of all of them)
+        if (wait_appends(e, -1) < 0) return SW_E_CUDA;
+        int rc = cansee_scan(e, e->stream, e->n_events);
         if (rc < 0) return rc;
-    }
+        CK(cudaEventRecord(e->scan_ev, e->stream));
+        e->scan_ev_set = true;
+    } else if (wait_appends(e, first + n) < 0) return SW_E_CUDA;
     {
         Span sp(e, 0);
         int rc;
-        if (e->divide_impl == 5)
-            rc = e->NC == 1 ? (e->unit ? divide_round_batch<1, true>(e, P) : divide_round_batch<1, false>(e, P))
-                            : (e->unit ? divide_round_batch<2, true>(e, P) : divide_round_batch<2, false>(e, P));
-        else if (e->divide_impl == 4) rc = divide_levels(e, P);
-        else rc = e->NC == 1 ? (e->unit ? launch_divide<1, true>(e, P) : launch_divide<1, false>(e, P))
-                             : (e->unit ? launch_divide<2, true>(e, P) : launch_divide<2, false>(e, P));
+        if (e->wide) rc = SW_NJ(divide_rounds_wide, e, first, n);
+        else rc = e->NC == 1 ? (e->unit ? divide_round_batch<1, true>(e, first, n) : divide_round_batch<1, false>(e, first, n))
+                             : (e->unit ? divide_round_batch<2, true>(e, first, n) : divide_round_batch<2, false>(e, first, n));
         if (rc < 0) return rc;
-        const int wpb = 8;
-        int blocks = (n + wpb - 1) / wpb;
-        if (e->divide_impl == 5) {                       // the round-batch path leaves the list of the chunk's witnesses
-            Q.list = e->d_cev + e->cap; Q.list_n = e->d_rbmeta + 225;
-            blocks = std::min(blocks, 4 * e->n_sm);
-        }
-        if (e->NC == 1) k_strong<1><<<blocks, wpb * 32, 0, e->stream>>>(Q);
-        else k_strong<2><<<blocks, wpb * 32, 0, e->stream>>>(Q);
-        CK(cudaGetLastError());
     }
-    e->stats.kernel_launches += e->divide_impl == 5 ? 1 : 2;      // k_strong (+ the walker; the round-batch kernels count themselves)
     e->stats.events_divided += n;
     e->n_divided += n;
     return SW_OK;
@@ -582,28 +669,33 @@ int sw_decide_fame(sw_engine *e, int32_t *new_c_out, int cap) {
     P.M = e->M; P.Rcap = e->Rcap; P.C = e->C; P.W = e->d_W; P.S = e->d_S; P.famous = e->d_famous;
     P.famous_ev = e->d_famous_ev; P.consensus = e->d_consensus; P.done = e->d_done; P.rem = e->d_rem;
     P.coin = e->d_coin; P.stake = e->d_stake; P.tot2 = 2 * e->tot; P.unit = e->unit ? 1 : 0; P.newc = e->d_newc; P.scal = e->d_scal;
+    P.Sw = e->d_Sw;
     {
         Span sp(e, 1);
         k_fame_begin<<<1, 32, 0, e->stream>>>(P);
-        k_fame_rounds<<<2 * e->n_sm, 256, 0, e->stream>>>(P);
+        if (e->wide) SW_NJ(fame_rounds_wide, e, P);
+        else k_fame_rounds<<<2 * e->n_sm, 256, 0, e->stream>>>(P);
         k_fame_finish<<<1, 1024, 0, e->stream>>>(P);
         CK(cudaGetLastError());
     }
     e->stats.kernel_launches += 3;
+    // one copy pair, one synchronisation: the scalars and (speculatively) the first new consensus rounds together
+    const int spec = std::min(e->Rcap, 64);
     CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_newc, e->d_newc, sizeof(int32_t) * spec, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     fold_spans(e);
-    e->stats.d2h_bytes += sizeof(int32_t) * SC_COUNT;
+    e->stats.d2h_bytes += sizeof(int32_t) * (SC_COUNT + spec);
     int rc = device_error(e);
     if (rc < 0) return rc;
     const int cnt = e->h_scal[SC_NEWC];
     if (cnt > cap) return fail(e, SW_E_ARG, "decide_fame: %d new consensus rounds do not fit cap=%d", cnt, cap);
-    if (cnt > 0) {
+    if (cnt > spec) {
         CK(cudaMemcpyAsync(e->h_newc, e->d_newc, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
-        memcpy(new_c_out, e->h_newc, sizeof(int32_t) * cnt);
         e->stats.d2h_bytes += sizeof(int32_t) * cnt;
     }
+    if (cnt > 0) memcpy(new_c_out, e->h_newc, sizeof(int32_t) * cnt);
     return cnt;
 }
 
@@ -614,13 +706,14 @@ int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
     std::vector<int32_t> rs(new_c, new_c + n);
     std::sort(rs.begin(), rs.end());                                  // sorted(new_c), swirld.py:283
     for (int r : rs) if (r < 0 || r >= e->Rcap) return fail(e, SW_E_KEY, "find_order: unknown round %d", r);
+    const size_t MS = e->MS;
     if (n > e->seg_cap) {
         int nc = std::max(n, std::max(64, 2 * e->seg_cap));
         for (void *p : {(void *)e->d_seg_start, (void *)e->d_seg_fw, (void *)e->d_seg_nf, (void *)e->d_seg_white, (void *)e->d_rounds_in, (void *)e->d_plan})
             if (p) cudaFree(p);
-        CK(dalloc(&e->d_seg_start, (size_t)nc + 1)); CK(dalloc(&e->d_seg_fw, (size_t)nc * 64));
+        CK(dalloc(&e->d_seg_start, (size_t)nc + 1)); CK(dalloc(&e->d_seg_fw, (size_t)nc * MS));
         CK(dalloc(&e->d_seg_nf, (size_t)nc)); CK(dalloc(&e->d_seg_white, (size_t)nc * 64));
-        CK(dalloc(&e->d_rounds_in, (size_t)nc)); CK(dalloc(&e->d_plan, (size_t)nc * 64 * 8));
+        CK(dalloc(&e->d_rounds_in, (size_t)nc)); CK(dalloc(&e->d_plan, (size_t)nc * MS * 8));
         e->seg_cap = nc;
     }
     CK(cudaMemcpyAsync(e->d_rounds_in, rs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
@@ -630,12 +723,19 @@ int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
     P.stake = e->d_stake; P.tot = e->tot; P.lastord = e->d_lastord; P.batch_ev = e->d_batch_ev; P.batch_seg = e->d_batch_seg;
     P.seg_start = e->d_seg_start; P.seg_fw = e->d_seg_fw; P.seg_nf = e->d_seg_nf; P.seg_white = e->d_seg_white;
     P.ts = e->d_ts; P.key = e->d_key; P.perm = e->d_perm; P.tx = e->d_tx; P.idx = e->d_idx; P.tx_base = e->n_tx; P.scal = e->d_scal;
-    P.plan = e->d_plan; P.plan_stride = e->seg_cap * 64;
+    P.plan = e->d_plan; P.plan_stride = (int)(e->seg_cap * MS);
+    const int M = e->M;
     cudaEvent_t a = get_event(e), b = get_event(e);
     cudaEventRecord(a, e->stream);
-    k_order_rounds<<<n, 1024, 0, e->stream>>>(P);
-    k_order_cuts<<<1, 64, 0, e->stream>>>(P);
-    k_order_list<<<std::max(1, std::min(4 * e->n_sm, (n * 64 + 255) / 256)), 256, 0, e->stream>>>(P);
+    if (e->wide) {
+        k_w_order_rounds<<<n, 1024, (size_t)3 * M * sizeof(int), e->stream>>>(P);
+        k_w_order_cuts<<<1, 1024, (size_t)2 * M * sizeof(int), e->stream>>>(P);
+        k_w_order_list<<<std::max(1, std::min(4 * e->n_sm, (int)(((size_t)n * M + 255) / 256))), 256, 0, e->stream>>>(P);
+    } else {
+        k_order_rounds<<<n, 1024, 0, e->stream>>>(P);
+        k_order_cuts<<<1, 64, 0, e->stream>>>(P);
+        k_order_list<<<std::max(1, std::min(4 * e->n_sm, (n * 64 + 255) / 256)), 256, 0, e->stream>>>(P);
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));      // rs (host vector) was consumed by the copy above
@@ -645,8 +745,13 @@ int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
     int rc = device_error(e);
     const int nbatch = e->h_scal[SC_BATCH];
     if (rc == 0 && nbatch > 0) {
-        const int wpb = 8;
-        k_order_times<<<(nbatch + wpb - 1) / wpb, wpb * 32, 0, e->stream>>>(P, nbatch);
+        if (e->wide) {
+            const size_t tsm = (size_t)OW_WARPS * M * sizeof(u64);
+            k_w_order_times<<<std::max(1, std::min(16 * e->n_sm, (nbatch + OW_WARPS - 1) / OW_WARPS)), OW_WARPS * 32, tsm, e->stream>>>(P, nbatch);
+        } else {
+            const int wpb = 8;
+            k_order_times<<<(nbatch + wpb - 1) / wpb, wpb * 32, 0, e->stream>>>(P, nbatch);
+        }
         k_order_sort<<<n, 1024, 0, e->stream>>>(P);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
@@ -753,6 +858,35 @@ int sw_flush_l2(sw_engine *e, int64_t bytes) {
         e->flush_bytes = (size_t)bytes;
     }
     CK(cudaMemsetAsync(e->d_flush, 0x5a, (size_t)bytes, e->stream));
+    return SW_OK;
+}
+
+// ---- several GPUs of one box: exchange buffers over NVLink peer memory (CUDA IPC, one process per GPU)
+int sw_peer_handle(sw_engine *e, void *handle_out64) {
+    if (!e || !handle_out64) return fail(e, SW_E_ARG, "bad argument");
+    if (!e->wide) return fail(e, SW_E_UNSUPPORTED, "the M <= 64 path does not shard (replicas only): no peer exchange");
+    CK(cudaSetDevice(e->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->d_xbuf));
+    memcpy(handle_out64, &h, 64);
+    return SW_OK;
+}
+
+int sw_peer_connect(sw_engine *e, int rank, int nranks, const void *handles) {
+    if (!e || !handles || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fail(e, SW_E_ARG, "bad argument");
+    if (!e->wide) return fail(e, SW_E_UNSUPPORTED, "the M <= 64 path does not shard (replicas only): no peer exchange");
+    if (e->n_divided > 0) return fail(e, SW_E_ARG, "sw_peer_connect: connect before the first divide_rounds");
+    CK(cudaSetDevice(e->device));
+    for (int p = 0; p < nranks; p++) {
+        if (p == rank) { e->x_peer[p] = e->d_xbuf; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const char *>(handles) + (size_t)64 * p, 64);
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        e->x_peer[p] = ptr;
+    }
+    e->rank = rank; e->nranks = nranks;
     return SW_OK;
 }
 

@@ -81,6 +81,8 @@ struct StrongParams {
     i64 tot2;
     int unit;
     const int32_t *list, *list_n;   // optional: the witnesses of the range (else every event of the range is looked at)
+    const unsigned *SMw;            // wide path (swirld_wide.cuh): SM as [cap][NJ] words, S as [Rcap][M][NJ] words
+    unsigned *Sw;
 };
 
 template <int NC>
@@ -156,6 +158,7 @@ struct FameParams {
     int unit;
     int32_t *newc;           // [Rcap] out
     int32_t *scal;
+    const unsigned *Sw;      // wide path: S as [Rcap][M][NJ] words
 };
 
 __global__ void k_fame_begin(FameParams P) {                    // one warp

@@ -23,7 +23,7 @@ SYMBOLS = [
     "sw_decide_fame", "sw_find_order", "sw_n_events", "sw_n_divided", "sw_max_round",
     "sw_n_transactions", "sw_get_round", "sw_get_witness_flags", "sw_get_famous", "sw_get_can_see",
     "sw_get_witness_table", "sw_get_consensus", "sw_get_transactions", "sw_get_idx", "sw_get_height",
-    "sw_sync", "sw_stats", "sw_flush_l2", "sw_version", "sw_debug_counters",
+    "sw_sync", "sw_stats", "sw_flush_l2", "sw_version", "sw_debug_counters", "sw_peer_handle", "sw_peer_connect",
 ]
 
 
@@ -79,6 +79,8 @@ def load_library(path: str = LIB_PATH):
     L.sw_flush_l2.argtypes = [vp, i64]
     L.sw_version.argtypes = []
     L.sw_debug_counters.argtypes = [vp, vp, i32]
+    L.sw_peer_handle.argtypes = [vp, vp]
+    L.sw_peer_connect.argtypes = [vp, i32, i32, vp]
     _lib = L
     return L
 

@@ -16,14 +16,24 @@ pytestmark = pytest.mark.gpu
 ALL = list(gs.SPECS)
 
 
+@pytest.fixture(params=["default", "wide"])
+def impl(request, monkeypatch):
+    """Both implementations of the path: the M <= 64 kernels (swirld_rounds.cuh / swirld_kernels.cuh) and the
+    any-M kernels of swirld_wide.cuh, which SW_FORCE_WIDE=1 selects for M <= 64 too (read by sw_create)."""
+    monkeypatch.setenv("SW_FORCE_WIDE", "1" if request.param == "wide" else "0")
+    return request.param
+
+
 def _run(tr, K, stake=None):
     from swirld_b200 import engine
     return engine.run_engine(tr, K, stake)
 
 
 @pytest.mark.parametrize("name", ALL)
-def test_engine_matches_reference_fixture(name):
+def test_engine_matches_reference_fixture(name, impl):
     tr, K, stake = gs.make_trace(name)
+    if impl == "wide" and tr.M > 64:
+        pytest.skip("M > 64 always runs the wide kernels")
     g = load_golden(name)
     r = _run(tr, K, stake)
     assert_same(g, r, what=name)
@@ -34,7 +44,7 @@ def test_engine_matches_reference_fixture(name):
 @pytest.mark.parametrize("M,N,K,seed", [
     (2, 300, 1, 1), (3, 500, 5, 2), (4, 1500, 1, 7), (5, 1500, 3, 8), (8, 4000, 64, 9), (13, 5000, 100, 10),
     (31, 6000, 999, 11), (32, 6000, 1000, 12), (33, 6000, 1001, 13), (48, 8000, 8000, 14), (64, 12000, 3000, 15)])
-def test_engine_matches_oracle_gossip(M, N, K, seed):
+def test_engine_matches_oracle_gossip(M, N, K, seed, impl):
     from swirld_b200 import traces
     tr = traces.gossip(M, N, seed)
     o = orc.run_oracle(tr, K)
@@ -46,7 +56,7 @@ def test_engine_matches_oracle_gossip(M, N, K, seed):
 @pytest.mark.parametrize("M,N,K,seed,pc,ps", [
     (4, 3000, 1, 21, 0.1, 0.3), (6, 4000, 17, 22, 0.05, 0.5), (16, 9000, 300, 23, 0.01, 0.3),
     (40, 9000, 2048, 24, 0.02, 0.4), (64, 12000, 4096, 25, 0.03, 0.3)])
-def test_engine_matches_oracle_adversarial(M, N, K, seed, pc, ps):
+def test_engine_matches_oracle_adversarial(M, N, K, seed, pc, ps, impl):
     from swirld_b200 import traces
     tr = traces.adversarial(M, N, seed, pc, ps)
     o = orc.run_oracle(tr, K)
@@ -56,7 +66,7 @@ def test_engine_matches_oracle_adversarial(M, N, K, seed, pc, ps):
 
 
 @pytest.mark.parametrize("M,N,K,seed", [(8, 3000, 40, 31), (64, 10000, 2500, 32)])
-def test_engine_matches_oracle_tick_and_tied(M, N, K, seed):
+def test_engine_matches_oracle_tick_and_tied(M, N, K, seed, impl):
     from swirld_b200 import traces
     for tr in (traces.tick(M, N, seed), traces.gossip(M, N, seed, tied=16)):
         o = orc.run_oracle(tr, K)
@@ -64,7 +74,7 @@ def test_engine_matches_oracle_tick_and_tied(M, N, K, seed):
         assert_same(o, r, what=tr.name)
 
 
-def test_engine_stake_and_coin_period():
+def test_engine_stake_and_coin_period(impl):
     from swirld_b200 import engine, traces
     tr = traces.gossip(9, 4000, 41)
     stake = [2, 1, 1, 1, 1, 1, 1, 1, 1]
@@ -152,7 +162,7 @@ def _properties(tr, r):
     assert np.all(r["witness"][r["famous"] >= 0] == 1)
 
 
-def test_engine_edge_cases():
+def test_engine_edge_cases(impl):
     """Empty calls, exact-fit and exhausted capacity, ragged schedules, 64 members x tiny chunks."""
     from swirld_b200 import engine, traces
     tr = traces.gossip(64, 3000, 77)
@@ -182,7 +192,7 @@ def test_engine_edge_cases():
         e.append([0], [1], [0], np.zeros(1), np.zeros((1, 64), np.uint8))
     assert ei.value.code in (-5, -7, -6)
     with pytest.raises(engine.EngineError):          # M above this build's limit
-        engine.Engine(65, 16)
+        engine.Engine(1025, 16)
 
 
 @pytest.mark.parametrize("M,N,K,gen", [(16, 100000, 4096, "gossip"), (64, 262144, 65536, "gossip"),
@@ -210,7 +220,7 @@ def test_append_everything_first(M, N, K, gen):
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
-def test_find_order_with_already_ordered_famous_witness(seed):
+def test_find_order_with_already_ordered_famous_witness(seed, impl):
     """Traces on which some consensus round has a famous witness that an earlier round already ordered
     (tests/test_order_model.py counts them): k_order_cuts must take the reach over the other witnesses."""
     from swirld_b200 import traces
@@ -218,3 +228,95 @@ def test_find_order_with_already_ordered_famous_witness(seed):
     o = orc.run_oracle(tr, 37)
     r = _run(tr, 37)
     assert_same(o, r, what=tr.name)
+
+
+# ---------------------------------------------------------------- beyond 64 members (swirld_wide.cuh)
+@pytest.mark.parametrize("gen,M,N,K,seed,stake", [
+    ("gossip", 65, 9000, 777, 61, None), ("gossip", 100, 16000, 4000, 62, None), ("adversarial", 130, 30000, 8192, 63, None),
+    ("tick", 200, 24000, 5000, 64, None), ("gossip", 256, 40000, 16384, 65, None), ("gossip", 300, 36000, 36000, 66, None),
+    ("gossip", 72, 9000, 500, 67, "mixed"), ("adversarial", 96, 12000, 1, 68, None)])
+def test_wide_engine_matches_oracle(gen, M, N, K, seed, stake):
+    from swirld_b200 import traces
+    tr = getattr(traces, gen)(M, N, seed)
+    if K == 1:
+        tr = tr.slice(0, 1500)                   # the reference's own cadence: one event per call
+    st = [1 + (i % 5 == 0) + 2 * (i % 7 == 3) for i in range(M)] if stake else None
+    o = orc.run_oracle(tr, K, st)
+    r = _run(tr, K, st)
+    assert_same(o, r, what=tr.name)
+    assert np.array_equal(o["oracle"].can_see(), r["can_see"])
+
+
+def test_wide_engine_1024_members_against_oracle():
+    """Config 5's member count on a prefix the literal oracle finishes in about a minute."""
+    from swirld_b200 import traces
+    tr = traces.gossip(1024, 40000, 9)
+    o = orc.run_oracle(tr, 20000)
+    r = _run(tr, 20000)
+    assert_same(o, r, what=tr.name)
+    assert np.array_equal(o["oracle"].can_see(), r["can_see"])
+
+
+# ---------------------------------------------------------------- the append-ahead pipeline (INTEGRATION.md section 3)
+@pytest.mark.parametrize("M,N,K,ahead", [(4, 2000, 50, 2), (16, 30000, 700, 3), (64, 60000, 5000, 2), (96, 30000, 3000, 2)])
+def test_append_ahead_from_pinned_memory(M, N, K, ahead):
+    """Chunks appended `ahead` calls before their divide_rounds, from page-locked memory (truly asynchronous copies),
+    on a fresh engine: small chunks take the lazy can_see scan, which must wait for EVERY appended batch."""
+    import torch
+    from swirld_b200 import engine, traces
+    from swirld_b200.traces import chunks
+    tr = traces.gossip(M, N, 71)
+    o = orc.run_oracle(tr, K)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(getattr(tr, k))).pin_memory().numpy() for k in ("p0", "p1", "creator", "t", "sig")}
+    sched = list(chunks(N, K))
+    e = engine.Engine(M, N)
+
+    def feed(i):
+        first, cnt = sched[i]
+        s = slice(first, first + cnt)
+        e.append(pin["p0"][s], pin["p1"][s], pin["creator"][s], pin["t"][s], pin["sig"][s])
+    for i in range(min(ahead, len(sched))):
+        feed(i)
+    ncs = []
+    for i, (first, cnt) in enumerate(sched):
+        e.divide_rounds(first, cnt)
+        if i + ahead < len(sched):
+            feed(i + ahead)
+        nc = e.decide_fame()
+        e.find_order(nc)
+        ncs.append(sorted(nc))
+    r = e.results()
+    r["new_c_per_call"] = ncs
+    assert_same(o, r, what="append-ahead " + tr.name)
+    assert np.array_equal(o["oracle"].can_see(), e.can_see())
+
+
+def test_lazy_scan_then_eager_scan_without_a_sync():
+    """append(small); divide_rounds (lazy scan on the compute stream, asynchronous); append(big) (eager scan on the
+    copy stream) with no synchronising call in between: the two scans share scratch and must not overlap."""
+    from swirld_b200 import engine, traces
+    tr = traces.gossip(32, 40000, 72)
+    o = orc.Oracle(32)
+    o.append(tr)
+    o.divide_rounds(0, tr.N)
+    e = engine.Engine(32, tr.N)
+    e.append_trace(tr, 0, 3000)
+    e.divide_rounds(0, 3000)
+    e.append_trace(tr, 3000, 30000)
+    e.divide_rounds(3000, 30000)
+    e.append_trace(tr, 33000, 7000)
+    e.divide_rounds(33000, 7000)
+    assert np.array_equal(o.can_see(), e.can_see())
+    assert np.array_equal(o.results()["round"], e.rounds())
+
+
+# ---------------------------------------------------------------- the headline configuration at full length
+def test_headline_config3_full_length():
+    """64 members x 1 000 000 events, K = 65 536 (BASELINE.json configs[2]) element-wise against the oracle."""
+    from swirld_b200 import traces
+    tr = traces.gossip(64, 1000000, 1)
+    o = orc.run_oracle(tr, 65536)
+    r = _run(tr, 65536)
+    assert_same(o, r, what="config 3 full length")
+    assert np.array_equal(witness_flags_from_table(o["witness_table"], tr.N), r["witness"])
+    _properties(tr, r)
