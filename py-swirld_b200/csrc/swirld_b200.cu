@@ -57,7 +57,7 @@ struct sw_engine {
     int n_rowed = 0;              // events whose can_see row is complete
     // can_see scan scratch (swirld_cansee.cuh)
     int4 *d_cs_meta = nullptr;
-    uint8_t *d_cs_wr = nullptr, *d_cs_xb = nullptr;
+    uint8_t *d_cs_wr = nullptr, *d_cs_xb = nullptr, *d_cs_sflag = nullptr;
     int32_t *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_carry = nullptr, *d_cs_slow = nullptr, *d_cs_slowcnt = nullptr;
     int cs_min_B = 256;           // smallest block length the scan uses (sizes the per-block scratch)
     double *d_t = nullptr;
@@ -231,7 +231,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     C.M = M; C.first = first; C.n = n;
     C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.stale = e->d_stale; C.row = e->d_row;
     C.meta = e->d_cs_meta; C.wr = e->d_cs_wr; C.xb = e->d_cs_xb; C.last = e->d_cs_last; C.Qtab = e->d_cs_Q;
-    C.carry = e->d_cs_carry; C.slow_list = e->d_cs_slow; C.slow_cnt = e->d_cs_slowcnt;
+    C.carry = e->d_cs_carry; C.slow_list = e->d_cs_slow; C.slow_cnt = e->d_cs_slowcnt; C.sflag = e->d_cs_sflag;
     cudaEvent_t a = get_event(e), b = get_event(e);
     int small_n = 24;
     if (const char *v = getenv("SW_CS_SMALL")) small_n = atoi(v);
@@ -253,6 +253,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     C.B = B;
     C.first_al = first & ~3;
     C.nb = (first + n <= C.first_al + B) ? 1 : 1 + (first + n - (C.first_al + B) + B - 1) / B;
+    if (C.nb > 1 && first + n - (C.first_al + (C.nb - 1) * B) < 3 * B / 4) C.nb--;     // a short tail joins the block before it
     const int ntiles = (M + CS_CT - 1) / CS_CT;
     const size_t smem = (size_t)M * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
     const int pblocks = std::max(1, std::min(8 * e->n_sm, (n + 255) / 256));
@@ -260,7 +261,8 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     if (C.nb > 1) {
         CK(cudaMemsetAsync(e->d_cs_wr + first, 0, (size_t)n, st));
         CK(cudaMemsetAsync(e->d_cs_xb + first, 0, (size_t)n, st));
-        CK(cudaMemsetAsync(e->d_cs_slowcnt, 0, sizeof(int32_t) * ((size_t)C.nb + 1), st));
+        CK(cudaMemsetAsync(e->d_cs_sflag + first, 0, (size_t)n, st));
+        CK(cudaMemsetAsync(e->d_cs_slowcnt, 0, sizeof(int32_t) * 2, st));
     }
     cudaEventRecord(a, st);
     k_cs_prep<<<pblocks, 256, 0, st>>>(C);
@@ -332,7 +334,7 @@ int divide_round_batch(sw_engine *e, int first, int n) {
     return 0;
 }
 
-size_t rounds_wide_smem(int M) { return (size_t)(2 * M + 14 * M + 1 + 32 + (RW_THREADS / 32) * M + 1) * sizeof(int); }
+size_t rounds_wide_smem(int M) { return (size_t)(2 * M + 16 * M + 1 + 32 + (RW_THREADS / 32) * M + 1) * sizeof(int); }
 
 // rounds of the chunk for any member count (swirld_wide.cuh)
 template <int NJ>
@@ -343,7 +345,9 @@ int divide_rounds_wide(sw_engine *e, int first, int n) {
     const int grid = e->n_sm;
     const int nw = grid * (RW_THREADS / 32);
     const int nown = (M + e->nranks - 1) / e->nranks;
-    R.L = std::max(2, std::min(RW_LMAX, 2 * nw / std::max(1, nown)));
+    // events per member below a step's frontier: about two tests per warp and step, never more than half a window
+    R.L = std::max(1, std::min(RW_LMAX / 2, 2 * nw * e->nranks / std::max(1, M)));
+    (void)nown;
     if (const char *v = getenv("SW_RW_L")) R.L = std::max(1, std::min(RW_LMAX, atoi(v)));
     R.epoch = ++e->rb_epoch;
     R.row = e->d_row; R.p0 = e->d_p0; R.creator = e->d_creator; R.seq = e->d_seq; R.round = e->d_round;
@@ -459,7 +463,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         if (const char *v = getenv("SW_CS_B")) e->cs_min_B = std::max(64, std::min(e->cs_min_B, atoi(v)));
         const size_t nbmax = cap / e->cs_min_B + 3;
         CK(dalloc(&e->d_cs_meta, cap)); CK(dalloc(&e->d_cs_wr, cap)); CK(dalloc(&e->d_cs_xb, cap)); CK(dalloc(&e->d_cs_slow, cap + 4));
-        CK(dalloc(&e->d_cs_last, nbmax * M)); CK(dalloc(&e->d_cs_Q, (nbmax + 1) * M)); CK(dalloc(&e->d_cs_slowcnt, nbmax + 1));
+        CK(dalloc(&e->d_cs_last, nbmax * M)); CK(dalloc(&e->d_cs_Q, (nbmax + 1) * M)); CK(dalloc(&e->d_cs_slowcnt, (size_t)4)); CK(dalloc(&e->d_cs_sflag, cap));
         CK(dalloc(&e->d_cs_carry, MP));
         CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, 2 * cap)); /* + the witness list of the current chunk */
         CK(dalloc(&e->d_rbmeta, std::max<size_t>(256, 3 * MP + 64)));
@@ -493,6 +497,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         const size_t cs_smem = (size_t)M * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
         CK(cudaFuncSetAttribute(k_cs_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         CK(cudaFuncSetAttribute(k_cs_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));
         return reset_state(e);
     }();
     if (rc < 0) { g_create_error = e->err; sw_destroy(e); return rc; }
@@ -512,7 +517,7 @@ void sw_destroy(sw_engine *e) {
     if (e->scan_ev) cudaEventDestroy(e->scan_ev);
     for (int p = 0; p < 8; p++) if (e->x_peer[p] && e->x_peer[p] != e->d_xbuf) cudaIpcCloseMemHandle(e->x_peer[p]);
     void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_carry,
-                    e->d_cs_meta, e->d_cs_wr, e->d_cs_xb, e->d_cs_slow, e->d_cs_slowcnt, e->d_stale, e->d_coin, e->d_dbg, e->d_height,
+                    e->d_cs_meta, e->d_cs_wr, e->d_cs_xb, e->d_cs_sflag, e->d_cs_slow, e->d_cs_slowcnt, e->d_stale, e->d_coin, e->d_dbg, e->d_height,
                     e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_SM,
                     e->d_scw, e->d_sctag, e->d_SMw, e->d_Sw, e->d_hitmin, e->d_xbuf, e->d_xstep,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_famous, e->d_consensus,

@@ -17,10 +17,10 @@
 //   heads   Q[j][m] = member m's latest event below block j (a scan of `last` over the blocks).
 //   check   every listed row (xb, or a member's last row), all blocks AT ONCE: a row whose out-of-block
 //           columns all show the member's head Q[j][c] itself is already final -- the head is the largest
-//           value column c can take below the block.  With B >= 16 M that is every listed row of a gossip
-//           graph; the others go to a per-block list and
-//   slow    are finished block after block from the final rows of the events they enter the lower blocks
-//           through (one CTA, normally an empty launch).
+//           value column c can take below the block.  With B >= 16 M that is all but ~0.1 % of the listed
+//           rows of a gossip graph; the others go to a list and
+//   slow    are finished, in dependency waves, from the final rows of the events they enter the lower
+//           blocks through (one CTA, a handful of rows or an empty launch).
 //   pass 2  the exact rows: the same walk with the cache preloaded with the final rows of the block-start
 //           heads; a stale other-parent (not its member's latest event: `stale`, from sw_append) is read
 //           from the table.  This is the only pass that writes the table.
@@ -39,18 +39,21 @@ struct CsParams {
     int32_t *last;              // [nb][M] last event of member m inside block j, -1 none (filled with -1 on entry)
     int32_t *Qtab;              // [nb+1][M] head of member m at the start of block j
     int32_t *carry;             // [M] heads before `first` (in/out)
-    int32_t *slow_list;         // [cap]: block j's slow rows live at [start(j), ...)
-    int32_t *slow_cnt;          // [nb] (+ [nb] = any), zero on entry
+    int32_t *slow_list;         // [cap] the listed rows that failed the check (any order)
+    int32_t *slow_cnt;          // [2]: their count, rows still pending; zero on entry
+    uint8_t *sflag;             // [cap] 0 final, 1 pending slow row, 2 finished by k_cs_slow, 3 finished in the running wave
 };
 
 #define CS_TILE 128
 #define CS_CT 32                // columns per tile = threads per CTA
 
+// (the last block takes whatever is left: a short tail block would fail the finality check often, so the host
+//  folds a tail shorter than 3B/4 into the block before it)
 __device__ __forceinline__ int cs_block_of(const CsParams &P, int h) {
-    return h < P.first_al + P.B ? 0 : (h - P.first_al) / P.B;
+    return h < P.first_al + P.B ? 0 : min((h - P.first_al) / P.B, P.nb - 1);
 }
 __device__ __forceinline__ int cs_start(const CsParams &P, int j) { return j == 0 ? P.first : P.first_al + j * P.B; }
-__device__ __forceinline__ int cs_end(const CsParams &P, int j) { return min(P.first_al + (j + 1) * P.B, P.first + P.n); }
+__device__ __forceinline__ int cs_end(const CsParams &P, int j) { return j == P.nb - 1 ? P.first + P.n : P.first_al + (j + 1) * P.B; }
 
 __global__ void __launch_bounds__(256) k_cs_prep(CsParams P) {
     const int end = P.first + P.n;
@@ -174,10 +177,13 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
         }
     }
     if (PASS == 1 && col) {                          // each member's last row of the block, from the cache
-        const int32_t *L = P.last + (size_t)blk * M;
-        for (int m = 0; m < M; m++) {
-            const int l = L[m];
-            if (l >= 0) rowc[(size_t)l * M] = val[m][lane];
+        const int32_t *__restrict__ L = P.last + (size_t)blk * M;
+        for (int m0 = 0; m0 < M; m0 += 8) {          // (eight loads in flight, then the stores: they may alias for the compiler)
+            int l[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) l[u] = m0 + u < M ? __ldg(L + m0 + u) : -1;
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (l[u] >= 0) rowc[(size_t)l[u] * M] = val[m0 + u][lane];
         }
     }
 }
@@ -186,10 +192,13 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
 __global__ void k_cs_heads(CsParams P) {
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < P.M; m += gridDim.x * blockDim.x) {
         int q = P.carry[m];
-        for (int j = 0; j < P.nb; j++) {
-            P.Qtab[(size_t)j * P.M + m] = q;
-            const int l = P.last[(size_t)j * P.M + m];
-            if (l >= 0) q = l;
+        for (int j0 = 0; j0 < P.nb; j0 += 16) {
+            int l[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) l[u] = j0 + u < P.nb ? __ldg(P.last + (size_t)(j0 + u) * P.M + m) : -1;
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+                if (j0 + u < P.nb) { P.Qtab[(size_t)(j0 + u) * P.M + m] = q; if (l[u] >= 0) q = l[u]; }
         }
         P.Qtab[(size_t)P.nb * P.M + m] = q;
         P.carry[m] = q;
@@ -221,33 +230,45 @@ __global__ void __launch_bounds__(256) k_cs_check(CsParams P) {
                 ok &= pr >= lim || pr == Q[c];
             }
             if (!__all_sync(0xffffffffu, ok) && lane == 0) {
-                const int slot = atomicAdd(&P.slow_cnt[bx], 1);
-                P.slow_list[lim + slot] = x;
-                P.slow_cnt[P.nb] = 1;
+                P.slow_list[atomicAdd(&P.slow_cnt[0], 1)] = x;
+                atomicAdd(&P.slow_cnt[1], 1);
+                P.sflag[x] = 1;
             }
         }
     }
 }
 
-// the rows that failed the check, block after block: row(x)[c] = max(partial, max over members m of the final
-// row of the event through which x enters m's chain below the block: the head Q[m] if x sees an in-block event
-// of m (or the head itself), else the direct out-of-block parent it shows)
-#define CS_SLOW_WARPS 8
+// The rows that failed the check: row(x)[c] = max(partial, max over members m of the FINAL row of the event through
+// which x enters m's chain below the block: the head Q[m] if x sees an in-block event of m (or the head itself),
+// else the direct out-of-block parent it shows).  Those events are listed rows of earlier blocks and nearly always
+// final already, so the rows are finished in waves: a row whose entry events are all final is finished now, the others
+// wait for the next wave (every wave finishes at least the pending rows of the lowest block).  One CTA; normally a
+// handful of rows, or none.
+#define CS_SLOW_WARPS 16
 __global__ void __launch_bounds__(CS_SLOW_WARPS * 32) k_cs_slow(CsParams P) {
     extern __shared__ int cs_smem[];
-    if (!P.slow_cnt[P.nb]) return;
+    const int cnt = P.slow_cnt[0];
+    if (cnt == 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, M = P.M;
     int *ent = cs_smem + (size_t)warp * M;                 // per warp: the entry event per member
-    for (int blk = 0; blk < P.nb; blk++) {
-        const int cnt = P.slow_cnt[blk], lim = cs_start(P, blk);
-        const int32_t *Q = P.Qtab + (size_t)blk * M;
+    __shared__ int left_s;
+    if (threadIdx.x == 0) left_s = cnt;
+    __syncthreads();
+    while (left_s > 0) {
         for (int i = warp; i < cnt; i += CS_SLOW_WARPS) {
-            const int x = P.slow_list[lim + i];
+            const int x = P.slow_list[i];
+            if (P.sflag[x] != 1) continue;
+            const int bx = cs_block_of(P, x), lim = cs_start(P, bx);
+            const int32_t *Q = P.Qtab + (size_t)bx * M;
+            bool ready = true;
             for (int m = lane; m < M; m += 32) {
                 const int pr = P.row[(size_t)x * M + m], q = Q[m];
-                ent[m] = (pr >= lim || pr == q) ? q : pr;
+                const int ev = (pr >= lim || pr == q) ? q : pr;
+                ent[m] = ev;
+                if (ev >= P.first) { const int f = P.sflag[ev]; ready &= !(f == 1 || f == 3); }
             }
             __syncwarp();
+            if (!__all_sync(0xffffffffu, ready)) continue;
             for (int c = lane; c < M; c += 32) {
                 const int pr = P.row[(size_t)x * M + c];
                 if (pr >= lim) continue;
@@ -259,8 +280,11 @@ __global__ void __launch_bounds__(CS_SLOW_WARPS * 32) k_cs_slow(CsParams P) {
                 if (acc != pr) P.row[(size_t)x * M + c] = acc;
             }
             __syncwarp();
+            if (lane == 0) { P.sflag[x] = 3; atomicSub(&left_s, 1); }
         }
-        __syncthreads();                                   // rows of this block are final before the next one reads them
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) { const int x = P.slow_list[i]; if (P.sflag[x] == 3) P.sflag[x] = 2; }
+        __syncthreads();
     }
 }
 

@@ -236,15 +236,17 @@ __device__ __forceinline__ u64 rw_ld_tag(const u64 *p) {
 template <int NJ>
 __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
     extern __shared__ int rw_smem[];
-    const int M = P.M, L = P.L;
+    const int M = P.M;
     // chain state, identical in every CTA (and on every rank)
     i64 *stake_s = reinterpret_cast<i64 *>(rw_smem);    // [M]
     int *cur = rw_smem + 2 * M, *pos = cur + M, *len = pos + M, *off = len + M, *cmin_s = off + M, *ctot_s = cmin_s + M;
     int *Wc = ctot_s + M, *Wn = Wc + M;                 // Wf of the current round and of the next one
-    int *lo_ev = Wn + M, *hi_ev = lo_ev + M;            // first / last event of a member whose S_r mask this step prepares
-    int *rlo = hi_ev + M, *rbase = rlo + M;             // prepared seq range: start, exclusive prefix of the counts (rbase[M] = total)
+    int *lo_ev = Wn + M, *hi_ev = lo_ev + M;            // first / last event of a member whose S_r mask is prepared
+    int *rlo = hi_ev + M, *rbase = rlo + M;             // masks to prepare this step: start seq, exclusive prefix of the counts (rbase[M] = total)
     int *s_nfin = rbase + M + 1, *s_base = s_nfin + M;
-    int *red = s_base + M;                              // [32] reduction scratch
+    int *pdone = s_base + M;                            // seq up to which a member's masks of round rprev are prepared (this launch)
+    int *ntest = pdone + M;                             // pending positions of the member tested this step
+    int *red = ntest + M;                               // [32] reduction scratch
     int *spre_all = red + 32;                           // [warps][M] per-warp staging of a test's pre[] row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * (RW_THREADS / 32) + warp, nw = gridDim.x * (RW_THREADS / 32);
@@ -253,6 +255,17 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
     const bool unit = P.unit != 0;
     int *spre = spre_all + (size_t)warp * M;
     u64 *xmine = P.nranks > 1 ? P.xhit[P.rank] : nullptr;   // my own exchange buffer (what the peers wrote for me)
+
+    auto block_min = [&](int v) -> int {                // min over the CTA (all threads call it)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        v = red[0];
+        for (int w2 = 1; w2 < RW_THREADS / 32; w2++) v = min(v, red[w2]);
+        return v;
+    };
 
     int rtop = max(P.scal[SC_MAX_ROUND], 0);
     const unsigned xbase = (P.nranks > 1 && lead) ? *P.xstep : 0u;      // (written back by CTA 0 after the last barrier)
@@ -279,13 +292,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
         // ---- lowest open round
         int rmin = 0x7fffffff;
         for (int c = tid; c < M; c += RW_THREADS) if (pos[c] < len[c]) rmin = min(rmin, cur[c]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
-        if (lane == 0) red[warp] = rmin;
-        __syncthreads();
-        rmin = red[0];
-        for (int w2 = 1; w2 < RW_THREADS / 32; w2++) rmin = min(rmin, red[w2]);
-        __syncthreads();
+        rmin = block_min(rmin);
         if (rmin == 0x7fffffff) break;
         if (rmin >= P.Rcap - 1) { if (lead && tid == 0) atomicMin(&P.scal[SC_ERR], -5); break; }
         // ---- Wf rows of rmin and rmin+1.  Only row rmin+1 is written during this launch (by the bookkeeping below,
@@ -295,48 +302,73 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
                 const int keep = Wn[c];
                 Wc[c] = (rmin == rprev + 1) ? keep : __ldcg(P.Wf + (size_t)rmin * M + c);
                 Wn[c] = __ldcg(P.Wf + (size_t)(rmin + 1) * M + c);
+                pdone[c] = 0;
             }
             rprev = rmin;
-            __syncthreads();
         }
+        // ---- the step's frontier: the pending events of the chains at rmin with an index below X are tested, and the
+        //      masks S_rmin of EVERY event below X are prepared first -- a tested event sees nothing at or above itself,
+        //      so every mask a test needs is there (nothing is left to chance or deferred)
+        int xmin = 0x7fffffff;
+        for (int c = tid; c < M; c += RW_THREADS)
+            if (pos[c] < len[c] && cur[c] == rmin) xmin = min(xmin, P.cev[off[c] + pos[c]]);
+        xmin = block_min(xmin);
+        const int X = xmin + P.L * M;
         const int buf = step % 3;
         const u64 tag = rw_tag(rmin, P.epoch);
-        // ---- (a) ranges of events whose masks S_rmin this step prepares: per member, from Wf_rmin[c] to the end of
-        //      its pending window
         for (int c = tid; c < M; c += RW_THREADS) {
+            // tested positions of this chain: its pending events below X (at most RW_LMAX)
+            int nt = 0, nbelow;
+            const bool active = pos[c] < len[c] && cur[c] == rmin;
+            const int32_t *ce = P.cev + off[c];
+            if (active) {
+                int a = 0, b = min(RW_LMAX, len[c] - pos[c]);
+                while (a < b) { const int mid = (a + b) >> 1; if (ce[pos[c] + mid] < X) a = mid + 1; else b = mid; }
+                nt = a;
+            }
+            ntest[c] = nt;
+            {   // the member's events of this chunk below X
+                int a = active ? pos[c] + nt : 0, b = len[c];
+                if (active && nt < min(RW_LMAX, len[c] - pos[c])) b = a;
+                while (a < b) { const int mid = (a + b) >> 1; if (ce[mid] < X) a = mid + 1; else b = mid; }
+                nbelow = a;
+            }
             int lo = 0, cnt = 0, le = 0x7fffffff, he = -1;
             const int w = Wc[c];
             if (w >= 0) {
                 lo = __ldcg(P.seq + w);
                 const int before = len[c] > 0 ? cmin_s[c] : ctot_s[c];      // seq of the member's first event of this chunk
                 if (lo < before) lo = max(lo, before - RW_RING);            // older events are not in the ring any more
-                const int hi = len[c] > 0 ? cmin_s[c] + min(len[c], pos[c] + L) : ctot_s[c];
-                cnt = max(0, min(hi - lo, RW_RING));
-                if (cnt > 0) {
+                const int hi = len[c] > 0 ? cmin_s[c] + nbelow : ctot_s[c];
+                const int start = max(lo, pdone[c]);                        // [lo, start) was prepared by earlier steps of this round
+                cnt = max(0, min(hi - start, RW_RING));
+                pdone[c] = start + cnt;
+                if (start + cnt > lo) {
                     auto ev_at = [&](int sq) -> int {
-                        if (len[c] > 0 && sq >= cmin_s[c]) return P.cev[off[c] + sq - cmin_s[c]];
+                        if (len[c] > 0 && sq >= cmin_s[c]) return ce[sq - cmin_s[c]];
                         return __ldcg(P.gchain + (size_t)c * RW_RING + (sq & (RW_RING - 1)));
                     };
-                    le = ev_at(lo); he = ev_at(lo + cnt - 1);
+                    le = ev_at(lo); he = ev_at(start + cnt - 1);
                 }
+                lo = start;
             }
             rlo[c] = lo; rbase[c] = cnt; lo_ev[c] = le; hi_ev[c] = he;
         }
         __syncthreads();
-        if (warp == 0) {                                // exclusive scan of the counts (M <= 32 * per-lane chunk)
+        if (warp == 0) {                                // exclusive scan of the counts
             const int per = (M + 31) / 32;
             const int b0 = lane * per, b1 = min(M, b0 + per);
-            int s = 0;
-            for (int c = b0; c < b1; c++) s += rbase[c];
-            int inc = s;
+            int sacc = 0;
+            for (int c = b0; c < b1; c++) sacc += rbase[c];
+            int inc = sacc;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-            int run = inc - s;
+            int run = inc - sacc;
             for (int c = b0; c < b1; c++) { const int v = rbase[c]; rbase[c] = run; run += v; }
             if (lane == 31) rbase[M] = inc;
         }
         __syncthreads();
-        {
+        {   // ---- (a) masks of the new events below the frontier
             const int total = rbase[M];
             for (int i = gw; i < total; i += nw) {
                 int a = 0, b = M;                       // member whose range holds candidate i: last c with rbase[c] <= i
@@ -346,18 +378,18 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
                 if (len[c] > 0 && sq >= cmin_s[c]) k = P.cev[off[c] + sq - cmin_s[c]];
                 else k = __ldcg(P.gchain + (size_t)c * RW_RING + (sq & (RW_RING - 1)));
                 if (k < 0) continue;
-                if (rw_ld_tag(P.sctag + k) == tag) continue;          // prepared by an earlier step of this round
+                if (rw_ld_tag(P.sctag + k) == tag) continue;          // prepared by an earlier launch step of this round
                 const unsigned word = seen_words<NJ>(P.row + (size_t)k * M, Wc, M, lane);
                 rw_publish<NJ>(P, k, word, tag, lane);
             }
         }
         rw_grid_barrier(P.bar, bar_target);
-        // ---- (b) tests: one warp per (chain, pending position); with several ranks, my share of the chains
+        // ---- (b) tests: one warp per (chain, tested position); with several ranks, my share of the chains
         {
             const int nown = (M - P.rank + P.nranks - 1) / P.nranks;
-            for (int i = gw; i < nown * L; i += nw) {
-                const int tc = (i / L) * P.nranks + P.rank, tj = i % L;
-                if (!(pos[tc] < len[tc] && cur[tc] == rmin && pos[tc] + tj < len[tc])) continue;
+            for (int i = gw; i < nown * RW_LMAX; i += nw) {
+                const int tc = (i / RW_LMAX) * P.nranks + P.rank, tj = i % RW_LMAX;
+                if (tj >= ntest[tc]) continue;
                 const int th = P.cev[off[tc] + pos[tc] + tj];
                 const int tpa = P.p0[th];
                 if (tpa < 0) continue;                                  // a root is never promoted
@@ -375,16 +407,15 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
                     }
                     if (unit) lv += __popc(__ballot_sync(0xffffffffu, live));
                     else {
-                        i64 s = live ? stake_s[c] : 0;
+                        i64 sacc = live ? stake_s[c] : 0;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                        lv += s;
+                        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                        lv += sacc;
                     }
                 }
                 __syncwarp();
                 if (lv <= thr) continue;                                // hits[c_] <= stake of the live members
-                // masks outside the prepared ranges (an event far ahead of its chain's window, or older than the ring):
-                // checked by tag, computed and published here when missing
+                // a mask outside the prepared ranges (an event older than the ring): checked by tag, computed here
                 for (int c0 = 0; c0 < M; c0 += 32) {
                     const int c = c0 + lane;
                     const int k = c < M ? spre[c] : -1;
@@ -440,18 +471,17 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
         bool opened = false;
         for (int c = tid; c < M; c += RW_THREADS) {
             int nfinal = 0, o = 0;
-            if (pos[c] < len[c] && cur[c] == rmin) {
-                const int win = min(L, len[c] - pos[c]);
+            if (ntest[c] > 0) {
                 const u64 hm = P.nranks > 1 ? __ldcg(xmine + ((size_t)(c % P.nranks) * 3 + buf) * M + c) : __ldcg(hsrc + c);
                 o = off[c] + pos[c];
                 if (hm != ~0ull) {
                     const int ft = (int)(hm >> 32), hnew = (int)(unsigned)hm;
-                    nfinal = ft;
+                    nfinal = ft;                        // the events before the first hit are final at rmin
                     cur[c] = rmin + 1;
                     Wn[c] = hnew;
                     if (lead) P.Wf[(size_t)(rmin + 1) * M + c] = hnew;
                     opened = true;
-                } else nfinal = win;
+                } else nfinal = ntest[c];
                 pos[c] += nfinal;
             }
             s_nfin[c] = nfinal; s_base[c] = o;
@@ -461,8 +491,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
             const int nb2 = (buf + 2) % 3;
             for (int c = tid; c < M; c += RW_THREADS) P.hitmin[(size_t)nb2 * M + c] = ~0ull;
         }
-        for (int i = blockIdx.x + gridDim.x * tid; i < M * L; i += gridDim.x * RW_THREADS) {
-            const int c = i / L, j = i % L;
+        for (int i = blockIdx.x + gridDim.x * tid; i < M * RW_LMAX; i += gridDim.x * RW_THREADS) {
+            const int c = i / RW_LMAX, j = i % RW_LMAX;
             if (j < s_nfin[c]) P.round[P.cev[s_base[c] + j]] = rmin;
         }
         __syncthreads();

@@ -180,3 +180,87 @@ def heights(tr: Trace) -> np.ndarray:
             hl[i] = max(hl[p0[i]], hl[p1[i]]) + 1
     h[:] = hl
     return h
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Vectorised generators for the large configurations (BASELINE.json configs 4 and 5: 4 M and 16 M events).
+# Same processes as G1 / G2 above, drawn from numpy's PCG64 instead of `random.Random` (so the traces differ
+# from gossip()/adversarial() with the same seed, but are just as reproducible), built without a Python loop
+# over the events: the head of member b "at time i" is the last event j < i with creator[j] == b, found by a
+# searchsorted over b's own event list.
+def _fast_sigs(seed: int, n: int) -> np.ndarray:
+    """64 signature bytes per event from a counter-based generator (blake2b per event is ~1 us: too slow at 16 M)."""
+    rng = np.random.Generator(np.random.Philox(key=seed ^ 0x5157))
+    return rng.integers(0, 256, size=(n, 64), dtype=np.uint8)
+
+
+def _finish_np(M, p0, p1, cr, seed, name):
+    n = len(p0)
+    return Trace(M, p0.astype(np.int32), p1.astype(np.int32), cr.astype(np.int32),
+                 np.arange(n, dtype=np.float64), _fast_sigs(seed, n), name)
+
+
+def _chain_lists(M, a):
+    """events of every member in index order: (order, starts) with order[starts[c]:starts[c+1]] = c's events."""
+    order = np.argsort(a, kind="stable")
+    starts = np.searchsorted(a[order], np.arange(M + 1))
+    return order, starts
+
+
+def gossip_np(M: int, N: int, seed: int = 1) -> Trace:
+    """G1 at scale: roots 0..M-1, then creator a ~ U(M), peer b ~ U(M) \\ {a}, parents (head[a], head[b])."""
+    assert M >= 2 and N >= M
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = np.concatenate([np.arange(M), rng.integers(0, M, N - M)])
+    b = rng.integers(0, M - 1, N)
+    b += b >= a
+    order, starts = _chain_lists(M, a)
+    pos = np.empty(N, np.int64)                      # position of event i in its creator's list
+    pos[order] = np.arange(N) - np.repeat(starts[:-1], np.diff(starts))
+    p0 = np.where(pos > 0, order[np.maximum(starts[a] + pos - 1, 0)], -1)
+    # head of b below i: number of b's events with index < i, minus one
+    p1 = np.empty(N, np.int64)
+    border, bstarts = _chain_lists(M, b)             # the events that chose peer c, in index order
+    for c in range(M):
+        idx = border[bstarts[c]:bstarts[c + 1]]
+        ev = order[starts[c]:starts[c + 1]]
+        k = np.searchsorted(ev, idx)                 # events of c strictly below idx (idx itself is not c's: b != a)
+        p1[idx] = ev[np.maximum(k - 1, 0)]
+    p0[:M] = -1
+    p1[:M] = -1
+    return _finish_np(M, p0, p1, a, seed, "G1np(M=%d,N=%d,seed=%d)" % (M, N, seed))
+
+
+def adversarial_np(M: int, N: int, seed: int = 1, p_cross: float = 0.02, p_stale: float = 0.3) -> Trace:
+    """G2 at scale: two cliques, cross-clique peer with probability p_cross, other-parent 1..7 events behind the
+    peer's head with probability p_stale (clamped at the peer's root): delayed fame and near-forks, no true forks."""
+    assert M >= 4 and N >= M
+    rng = np.random.Generator(np.random.PCG64(seed))
+    half = M // 2
+    a = np.concatenate([np.arange(M), rng.integers(0, M, N - M)])
+    low = a < half
+    cross = rng.random(N) < p_cross
+    lo_own = np.where(low, 0, half)
+    n_own = np.where(low, half, M - half)
+    lo_oth = np.where(low, half, 0)
+    n_oth = np.where(low, M - half, half)
+    u = rng.random(N)
+    b_cross = lo_oth + np.minimum((u * n_oth).astype(np.int64), n_oth - 1)
+    b_own = lo_own + np.minimum((u * (n_own - 1)).astype(np.int64), n_own - 2)
+    b_own += b_own >= a
+    b = np.where(cross, b_cross, b_own)
+    back = np.where(rng.random(N) < p_stale, 1 + rng.integers(0, 7, N), 0)
+    order, starts = _chain_lists(M, a)
+    pos = np.empty(N, np.int64)
+    pos[order] = np.arange(N) - np.repeat(starts[:-1], np.diff(starts))
+    p0 = np.where(pos > 0, order[np.maximum(starts[a] + pos - 1, 0)], -1)
+    p1 = np.empty(N, np.int64)
+    border, bstarts = _chain_lists(M, b)
+    for c in range(M):
+        idx = border[bstarts[c]:bstarts[c + 1]]
+        ev = order[starts[c]:starts[c + 1]]
+        k = np.searchsorted(ev, idx) - 1             # the peer's head below idx
+        p1[idx] = ev[np.maximum(k - back[idx], 0)]
+    p0[:M] = -1
+    p1[:M] = -1
+    return _finish_np(M, p0, p1, a, seed, "G2np(M=%d,N=%d,seed=%d,pc=%g,ps=%g)" % (M, N, seed, p_cross, p_stale))

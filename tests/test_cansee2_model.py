@@ -33,6 +33,8 @@ def scan_launch(tr, stale, first, n, B, row, carry, stats):
     while nxt < first + n:
         starts.append(nxt)
         nxt += B
+    if len(starts) > 1 and first + n - starts[-1] < 3 * B // 4:
+        starts.pop()                                  # a short tail joins the block before it
     nb = len(starts)
     ends = starts[1:] + [first + n]
     blk_of = np.zeros(N, np.int64)
@@ -95,18 +97,29 @@ def scan_launch(tr, stale, first, n, B, row, carry, stats):
                 stats["fast"] += 1
             else:
                 slow[j].append(x)
-    for j in range(nb):
-        for x in slow[j]:
-            stats["slow"] += 1
+    # in dependency waves: a row is finished when every event it enters the lower blocks through is final
+    pending = {x: j for j in range(nb) for x in slow[j]}
+    while pending:
+        snapshot = set(pending)
+        done_now = []
+        for x, j in pending.items():
             pr = row[x].copy()
             inb = pr >= starts[j]
+            ent = [Q[j, m] if (inb[m] or pr[m] == Q[j, m]) else pr[m] for m in range(M)]
+            if any(e in snapshot for e in ent):
+                continue
+            stats["slow"] += 1
             acc = pr.copy()
-            for m in range(M):
-                e = Q[j, m] if (inb[m] or pr[m] == Q[j, m]) else pr[m]
+            for e in ent:
                 if e >= 0:
                     assert e < starts[j]
-                    acc = np.maximum(acc, row[e])          # final: an earlier block / launch
-            row[x] = np.where(inb, pr, acc)
+                    acc = np.maximum(acc, row[e])
+            done_now.append((x, np.where(inb, pr, acc)))
+        assert done_now, "a wave must finish at least the lowest block's rows"
+        for x, v in done_now:                       # (rows finished in a wave are not read in the same wave)
+            row[x] = v
+            del pending[x]
+        stats["waves"] = stats.get("waves", 0) + 1
     # ---- pass 2: the exact rows; out-of-block parents contribute their final rows
     for j in range(nb):
         s = starts[j]

@@ -13,3 +13,13 @@ def test_two_rank_gloo_plumbing():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_two_rank_sharded_round_steps():
+    """The chain-sharded round steps of k_rounds_wide (sw_peer_connect) as a CPU model over gloo, world size 2."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "_gloo_shard_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SHARD_OK" in out.stdout

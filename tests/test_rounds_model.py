@@ -10,8 +10,15 @@ from swirld_b200 import traces
 
 
 class RoundBatch:
-    def __init__(self, tr, rows, stake=None, L=8):
+    """L: pending events tested per chain and step (swirld_rounds.cuh).  frontier=True: the windows of
+    swirld_wide.cuh instead -- the pending events with an index below X = (lowest pending index at rmin) + L*M,
+    at most LMAX per chain.  exchange: callable(step results of MY chains) -> results of all chains (several
+    ranks: every rank evaluates P only for the chains c with c % nranks == rank)."""
+    LMAX = 32
+
+    def __init__(self, tr, rows, stake=None, L=8, frontier=False, rank=0, nranks=1, exchange=None):
         self.tr, self.M, self.rows, self.L = tr, tr.M, rows, L
+        self.frontier, self.rank, self.nranks, self.exchange = frontier, rank, nranks, exchange
         self.stake = [1] * tr.M if stake is None else list(stake)
         self.tot2 = 2 * sum(self.stake)
         self.round = np.full(tr.N, -1, np.int64)
@@ -58,12 +65,19 @@ class RoundBatch:
             r = min(cur[c] for c in act)
             self.steps += 1
             opened = {}
-            for c in act:
-                if cur[c] != r:
-                    continue
-                win = chains[c][pos[c]:pos[c] + self.L]
-                res = [tr.p0[h] >= 0 and self.P(h, r) for h in win]
-                ft = next((i for i, v in enumerate(res) if v), None)
+            at_r = [c for c in act if cur[c] == r]
+            if self.frontier:
+                X = min(chains[c][pos[c]] for c in at_r) + self.L * M
+                wins = {c: [h for h in chains[c][pos[c]:pos[c] + self.LMAX] if h < X] for c in at_r}
+            else:
+                wins = {c: chains[c][pos[c]:pos[c] + self.L] for c in at_r}
+            # first hit per chain: my share of the chains, then the exchange
+            mine = {c: next((i for i, h in enumerate(wins[c]) if tr.p0[h] >= 0 and self.P(h, r)), None)
+                    for c in at_r if c % self.nranks == self.rank}
+            hits = self.exchange(mine) if self.exchange else mine
+            for c in at_r:
+                win = wins[c]
+                ft = hits[c]
                 for h in win[:len(win) if ft is None else ft]:
                     self.round[h] = r
                 pos[c] += len(win) if ft is None else ft
@@ -92,3 +106,10 @@ def test_round_batch_equals_oracle(gen, M, N, chunks, stake, L):
         rb.divide(first, n)
         first += n
     assert np.array_equal(rb.round, o.results()["round"])
+    # the frontier windows of swirld_wide.cuh give the same rounds
+    rf = RoundBatch(tr, o.can_see(), stake, max(1, L // 4), frontier=True)
+    first = 0
+    for n in chunks:
+        rf.divide(first, n)
+        first += n
+    assert np.array_equal(rf.round, o.results()["round"])
