@@ -3,44 +3,43 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3]
 
-A "step" is one pass of the hot path over the whole synthetic trace of the
-workload: for every chunk of the pinned call schedule, `divide_rounds(chunk)` then
-`decide_fame()` (swirld.py:325-327), starting from an engine whose consensus state
-was cleared.  Workloads (BASELINE.json `configs`):
-    c1  4 members,  2 000 events, K=50      (plumbing)
-    c2  16 members, 100 000 events, K=4096
-    c3  64 members, 1 000 000 events, K=65536   <- headline, default
-Trace: generator G1 (reference-sim gossip), seed 1 + rank.
+A "step" is one pass of the hot path over the whole synthetic trace of the workload: for every
+chunk of the pinned call schedule, `divide_rounds(chunk)` then `decide_fame()` (swirld.py:325-327),
+starting from an engine whose consensus state was cleared.  Workloads (BASELINE.json `configs`):
+    c1  4 members,     2 000 events, K=50        G1 (plumbing)
+    c2  16 members,  100 000 events, K=4096      G1
+    c3  64 members, 1 000 000 events, K=65536    G1   <- headline, default
+    c4  256 members, 4 000 000 events, K=262144  G1 (vectorised generator)
+    c5  1024 members, 16 000 000 events, K=262144  G2 adversarial (two cliques, p_cross 0.02, stale other-parents 0.3)
+`--events` runs a prefix of the workload's event count.
 
-`value`   : events/s with the event columns already resident in HBM (sw_rewind keeps
-            them), device-timed with CUDA events on the engine's stream.
-`e2e`     : same metric through the C ABI from HOST buffers: every step clears the
-            engine, appends each chunk from pinned host memory (H2D inside the timed
-            region), runs divide_rounds + decide_fame per chunk and reads back
-            round / witness / famous for all events (D2H inside the timed region).
-`roofline`: the dominant kernel k_rounds_batch (round numbers of a chunk on the whole GPU, one
-            cooperative launch per divide_rounds call): algorithmic bytes 4M + 8 + 5 + M/8 per
-            event (read the event's can_see row, p0 and creator; write round, witness flag and
-            seen-mask: SURVEY.md section 8d's B(M) minus the can_see part B1(M), plus the row
-            read that a separate kernel cannot avoid) over its mean launch duration (CUDA
-            events on the engine's stream), against MEASURED_PEAKS.json hbm_gbs.
-`roofline_can_see`: the same for the can_see kernel family k_cs_* (SURVEY.md section 8d's
-            B1(M) = 12M + 12 bytes per event), the bandwidth-bound part of the path.
-`cpu_baseline` / --impl reference: the reference is pure Python and cannot travel to
-            the GPU box, so the CPU arm is the literal C restatement oracle/
-            (kind "port"), single-threaded per node-view like the reference
-            (README.md:27-28); at N > 1 it runs the N replicas of the GPU arm's workload in
-            N parallel processes (cores = N).
+`value`   : events/s with the event columns already resident in HBM (sw_rewind keeps them),
+            device-timed with CUDA events on the engine's stream; max over ranks.
+`e2e`     : the same metric through the C ABI from HOST buffers: every step clears the engine, appends each chunk
+            from pinned host memory (H2D inside the timed region), runs divide_rounds + decide_fame per chunk and
+            reads back round / witness / famous for all events (D2H inside the timed region).
+`parity`  : the engine's round / witness / famous (c1-c3: of the whole trace; c4-c5: of a prefix run with the prefix
+            as one chunk) compared element-wise with the oracle's, in this run.  A mismatch exits non-zero.
+`roofline`: the dominant kernel of the step (M <= 64: k_rounds_batch; above: k_rounds_wide or the can_see scan,
+            whichever takes longer) -- algorithmic bytes per event over its mean launch
+            duration (CUDA events on the engine's stream) against MEASURED_PEAKS.json hbm_gbs.
+`roofline_can_see`: the same for the can_see kernel family k_cs_* (B1(M) = 12M + 12 bytes per event).
+`cpu_baseline` / --impl reference: the literal C restatement oracle/ (kind "port"), single-threaded per node-view
+            like the reference (README.md:27-28), plus -- where baseline/_ref holds the staged reference files --
+            the UNMODIFIED Python reference timed on a prefix of the same trace (`python_reference`).
 
-N > 1: one process per GPU (torchrun), each rank runs an independent node-view
-(its own trace, seed 1 + rank) -- the path has no cross-GPU exchange at M <= 64
-("replicas"), so scaling is weak and there is no collective
-on the data path; ranks meet at a barrier before and after the timed region and
-the time is the max over ranks.
+N > 1, one process per GPU (torchrun):
+  c1-c3 (M <= 64): independent node-views ("replicas", DESIGN.md section 6: a round step costs less than any
+          cross-GPU exchange), own trace per rank, no collective on the data path, scaling "weak";
+  c4-c5 (M > 64): ONE hashgraph on all ranks: the P_r tests of every round step are sharded by member chain and the
+          ranks write their first hits into each other's buffers over NVLink from inside k_rounds_wide
+          (sw_peer_connect; handles exchanged once through torch.distributed); scaling "strong".
+Ranks meet at a barrier before and after the timed region and the time is the max over ranks.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -54,16 +53,18 @@ sys.path.insert(0, os.path.join(ROOT, "py-swirld_b200"))
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    "c1": dict(M=4, N=2000, K=50),
-    "c2": dict(M=16, N=100000, K=4096),
-    "c3": dict(M=64, N=1000000, K=65536),
+    "c1": dict(M=4, N=2000, K=50, gen="gossip"),
+    "c2": dict(M=16, N=100000, K=4096, gen="gossip"),
+    "c3": dict(M=64, N=1000000, K=65536, gen="gossip"),
+    "c4": dict(M=256, N=4000000, K=262144, gen="gossip_np"),
+    "c5": dict(M=1024, N=16000000, K=262144, gen="adversarial_np"),
 }
+GEN_TEXT = {"gossip": "G1 reference-sim gossip", "gossip_np": "G1 reference-sim gossip (vectorised generator)",
+            "adversarial_np": "G2 adversarial gossip (two cliques, p_cross 0.02, stale other-parents 0.3; vectorised generator)"}
 
-
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at c3 (65536 events), from the committed
-# ncu --set full captures under profiles/ (see profiles/README.md)
-ROUNDS_DRAM_BYTES_PER_LAUNCH = 18547712 + 2816        # k_rounds_batch (profiles/r01c_ncu_full.md)
-WALKER_DRAM_BYTES_PER_LAUNCH = 2365952 + 2083072      # k_divide_levels (SW_DIVIDE_IMPL=4)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at c3 (65536 events), from the
+# committed ncu --set full capture (profiles/README.md); None where no capture of that launch shape exists
+DRAM_BYTES_PER_LAUNCH = {("k_rounds_batch", 64, 65536): 18547712 + 2816}
 
 
 def algorithmic_bytes_per_event(M):
@@ -77,7 +78,7 @@ def can_see_bytes_per_event(M):
 
 
 def rounds_bytes_per_event(M):
-    """k_rounds_batch: read row(h), p0, creator; write round, witness flag, seen-mask."""
+    """the round kernel: read row(h), p0, creator; write round, witness flag, seen-mask."""
     return 4 * M + 8 + 5 + M / 8.0
 
 
@@ -132,40 +133,79 @@ class ClockSampler:
 
 def make_trace(wl, seed):
     from swirld_b200 import traces
-    cache = "/tmp/swirld_trace_M%d_N%d_s%d.npz" % (wl["M"], wl["N"], seed)
+    gen = wl.get("gen", "gossip")
+    cache = "/tmp/swirld_trace_%s_M%d_N%d_s%d.npz" % (gen, wl["M"], wl["N"], seed)
     if os.path.exists(cache):
         try:
             z = np.load(cache)
-            return traces.Trace(wl["M"], z["p0"], z["p1"], z["creator"], z["t"], z["sig"], "G1 cached")
+            return traces.Trace(wl["M"], z["p0"], z["p1"], z["creator"], z["t"], z["sig"], gen + " cached")
         except Exception:
             pass
-    tr = traces.gossip(wl["M"], wl["N"], seed)
-    try:
-        np.savez(cache, p0=tr.p0, p1=tr.p1, creator=tr.creator, t=tr.t, sig=tr.sig)
-    except Exception:
-        pass
+    tr = getattr(traces, gen)(wl["M"], wl["N"], seed)
+    if wl["N"] <= 2000000:
+        try:
+            tmp = cache + ".%d.tmp.npz" % os.getpid()
+            np.savez(tmp, p0=tr.p0, p1=tr.p1, creator=tr.creator, t=tr.t, sig=tr.sig)
+            os.replace(tmp, cache)
+        except Exception:
+            pass
     return tr
+
+
+def sharded(wl):
+    """M > 64: one hashgraph over all ranks (strong scaling); else independent node-views (weak)."""
+    return wl["M"] > 64
 
 
 # --------------------------------------------------------------------------- CPU arm
 def run_cpu_pass(tr, K, limit=None):
     """One pass of divide_rounds + decide_fame (+ find_order, untimed) through the
-    oracle port; returns (events, seconds in dr+df)."""
+    oracle port; returns (events, seconds in dr+df, seconds in find_order, results)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     n = tr.N if limit is None else min(limit, tr.N)
     res = orc.run_oracle(tr.slice(0, n), K)
     res["oracle"].close()
-    return n, res["t_divide_rounds"] + res["t_decide_fame"], res["t_find_order"]
+    return n, res["t_divide_rounds"] + res["t_decide_fame"], res["t_find_order"], res
+
+
+def port_rate_guess(M):
+    """events/s of the C port on one core (measured: 2.3e5 at M=64; the literal loops are O(M^2) per event)."""
+    return 2.3e5 * (64.0 / max(M, 4)) ** 2 if M >= 64 else 2.3e5 * min(16.0, (64.0 / M))
 
 
 def reference_sample_events(wl, steps):
-    """Events per step of the CPU arm: the whole trace when the run stays within about a minute of CPU work
-    (the port does ~2e5 events/s on one core), else a prefix of whole chunks."""
-    budget = int(60 * 2.0e5 / max(1, steps))
+    """Events per step of the CPU arm: the whole trace when the run stays within about a minute of CPU work,
+    else a prefix (whole chunks where a chunk fits)."""
+    budget = int(45 * port_rate_guess(wl["M"]) / max(1, steps))
     if budget >= wl["N"]:
         return wl["N"]
-    return max(wl["K"], budget // wl["K"] * wl["K"])
+    if budget >= wl["K"]:
+        return budget // wl["K"] * wl["K"]
+    return max(2000, min(wl["K"], budget))
+
+
+def python_reference_sample(tr, wl):
+    """The UNMODIFIED Python reference (staged under baseline/_ref by __graft_entry__.build()) on a prefix of the
+    trace: events/s through its own divide_rounds + decide_fame.  None when the files did not travel."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "swirld.py")):
+        return None
+    os.environ["SWIRLD_REFERENCE"] = ref
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_harness as rh
+        M = wl["M"]
+        n = min(tr.N, max(2000, int(12 * 5.6e3 * (64.0 / max(M, 8)) ** 2)))     # ~10-20 s of CPython
+        K = min(wl["K"], 2000) if n > 2000 else wl["K"]
+        r = rh.run_reference(tr.slice(0, n), K)
+        s = r["t_divide_rounds"] + r["t_decide_fame"]
+        return {"value": n / s, "unit": "events/s", "cores": 1, "kind": "reference-python",
+                "sample": "first %d events, K=%d, unmodified swirld.py (baseline/_ref) through oracle/ref_harness.py, "
+                          "divide_rounds %.2f s + decide_fame %.2f s (find_order %.2f s not counted)" % (
+                              n, K, r["t_divide_rounds"], r["t_decide_fame"], r["t_find_order"])}
+    except Exception as ex:      # the reference arm must not take the bench down
+        return {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
 
 
 def _reference_replica(job):
@@ -174,11 +214,11 @@ def _reference_replica(job):
     tr = make_trace(wl, seed)
     limit = reference_sample_events(wl, steps)
     if warm:
-        run_cpu_pass(tr, wl["K"], limit=min(tr.N, 50000))
+        run_cpu_pass(tr, wl["K"], limit=min(limit, 50000))
     t0 = time.perf_counter()
     tot_e, tot_s, t_fo = 0, 0.0, 0.0
     for _ in range(steps):
-        n, s, fo = run_cpu_pass(tr, wl["K"], limit)
+        n, s, fo, _ = run_cpu_pass(tr, wl["K"], limit)
         tot_e += n
         tot_s += s
         t_fo += fo
@@ -186,51 +226,61 @@ def _reference_replica(job):
 
 
 def bench_reference(args, wl, rank, world):
-    """The CPU arm on the workload of the GPU arm: `world` independent node-views (replicas), one host core
-    each -- the reference is single-threaded per node (README.md:27-28), so replicas are the only way it
-    can use more cores."""
+    """The CPU arm on the workload of the GPU arm.  Replica workloads (M <= 64): `world` independent node-views, one
+    host core each -- the reference is single-threaded per node (README.md:27-28), so replicas are the only way it can
+    use more cores.  Sharded workloads (M > 64): the GPU arm runs ONE graph however many GPUs it has, and so does
+    this arm (one core: the algorithm is sequential in the events)."""
     if rank != 0:
         return
-    jobs = [(wl, rank_seed(r), args.steps, args.warmup >= 1) for r in range(world)]
-    if world == 1:
+    nrep = 1 if sharded(wl) else world
+    jobs = [(wl, rank_seed(r, wl), args.steps, args.warmup >= 1) for r in range(nrep)]
+    if nrep == 1:
         res = [_reference_replica(jobs[0])]
     else:
         import concurrent.futures as cf
         import multiprocessing as mp
-        with cf.ProcessPoolExecutor(world, mp_context=mp.get_context("spawn")) as ex:
+        with cf.ProcessPoolExecutor(nrep, mp_context=mp.get_context("spawn")) as ex:
             res = list(ex.map(_reference_replica, jobs))
     tot_e = sum(r[0] for r in res)
     slow = max(r[1] for r in res)                # the job is as slow as its slowest replica
     t_fo = max(r[2] for r in res)
     v = tot_e / slow
+    sample = reference_sample_events(wl, args.steps)
     line = {
         "impl": "reference", "metric": "events/sec divide_rounds+decide_fame", "value": v, "unit": "events/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * slow / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(wl, world),
-        "cpu_baseline": {"value": v, "unit": "events/s", "cores": world, "kind": "port",
-                         "sample": "first %d of %d events x %d passes per replica, %d replica(s) in parallel processes, "
-                                   "oracle/swirld_oracle.c (literal C restatement; the Python reference cannot travel to "
-                                   "the GPU box), host has %d cpus" % (reference_sample_events(wl, args.steps), wl["N"],
-                                                                      args.steps, world, os.cpu_count())},
+        "higher_is_better": True, "scaling": "strong" if sharded(wl) else "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": workload_config(wl, world),
+        "cpu_baseline": {"value": v, "unit": "events/s", "cores": nrep, "kind": "port",
+                         "sample": "first %d of %d events x %d passes per node-view, %d node-view(s) in parallel processes, "
+                                   "oracle/swirld_oracle.c (literal C restatement of swirld.py:187-277, pinned to the "
+                                   "reference by tests/golden), host has %d cpus" % (sample, wl["N"], args.steps, nrep,
+                                                                                    os.cpu_count())},
         "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "find_order_events_per_s": tot_e / t_fo if t_fo > 0 else None,
+        "python_reference": python_reference_sample(make_trace(wl, rank_seed(0, wl)), wl),
     }
     print(json.dumps(line), flush=True)
 
 
 def workload_config(wl, world):
-    return {"workload": "G1 reference-sim gossip trace, %d members x %d events, call schedule K=%d events per "
-                        "(divide_rounds, decide_fame) pair, unit stake, coin period 6" % (wl["M"], wl["N"], wl["K"]),
-            "members": wl["M"], "events": wl["N"], "chunk": wl["K"],
-            "parallelism": "replicas x%d (independent node-views, no collective)" % world,
-            "l2": "L2 flushed (256 MiB device memset) before every timed step; per-step working set "
-                  "(can_see + T tables) also exceeds L2 at c3"}
+    par = ("one hashgraph on %d GPU(s): round-step tests sharded by member chain, first hits exchanged by P2P stores "
+           "over NVLink inside the round kernel" % world) if sharded(wl) else \
+          ("replicas x%d (independent node-views, no collective)" % world)
+    return {"workload": "%s trace, %d members x %d events, call schedule K=%d events per (divide_rounds, decide_fame) "
+                        "pair, unit stake, coin period 6" % (GEN_TEXT.get(wl.get("gen", "gossip"), wl.get("gen")),
+                                                            wl["M"], wl["N"], wl["K"]),
+            "members": wl["M"], "events": wl["N"], "chunk": wl["K"], "parallelism": par,
+            "l2": "L2 flushed (256 MiB device memset) before every timed step; the per-step working set (can_see "
+                  "table) also exceeds L2 from c3 up"}
 
 
 # --------------------------------------------------------------------------- multi-rank plumbing
-def rank_seed(rank):
-    """Every rank advances its own node-view: an independent trace."""
+def rank_seed(rank, wl=None):
+    """Replica workloads: every rank advances its own node-view (an independent trace).  Sharded workloads: all
+    ranks hold the same graph."""
+    if wl is not None and sharded(wl):
+        return 1
     return 1 + rank
 
 
@@ -243,9 +293,17 @@ def max_over_ranks(values, dist, device):
     return [float(x) for x in t.tolist()]
 
 
-def whole_job_rate(world, events_per_rank_step, steps, ms_max):
-    """events/s of the whole job: all ranks' events over the slowest rank's time."""
-    return world * events_per_rank_step * steps / (ms_max * 1e-3)
+def whole_job_rate(world, events_per_rank_step, steps, ms_max, shard=False):
+    """events/s of the whole job: all ranks' events over the slowest rank's time (one shared graph when sharded)."""
+    return (1 if shard else world) * events_per_rank_step * steps / (ms_max * 1e-3)
+
+
+def connect_peers(eng, dist, rank, world):
+    """sw_peer_connect: exchange the CUDA IPC handles of the engines' exchange buffers once, out of band."""
+    mine = eng.peer_handle()
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    eng.peer_connect(rank, world, b"".join(parts))
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -267,7 +325,8 @@ def bench_ours(args, wl, rank, world, local_rank):
         torch.cuda.synchronize()
 
     M, N, K = wl["M"], wl["N"], wl["K"]
-    tr = make_trace(wl, rank_seed(rank))
+    shard = sharded(wl)
+    tr = make_trace(wl, rank_seed(rank, wl))
     # pinned host copies of the event columns (the e2e leg's source)
     pin = {}
     for k in ("p0", "p1", "creator", "t", "sig"):
@@ -278,6 +337,8 @@ def bench_ours(args, wl, rank, world, local_rank):
     out_fam = torch.empty(N, dtype=torch.int8).pin_memory().numpy()
 
     eng = engine.Engine(M, N, device=local_rank)
+    if shard and world > 1:
+        connect_peers(eng, dist, rank, world)
     sched = list(chunks(N, K))
 
     def append_all():
@@ -291,6 +352,8 @@ def bench_ours(args, wl, rank, world, local_rank):
         eng.rewind()
         eng.flush_l2()
         l0 = eng.stats()["kernel_launches"]       # (syncs; before the timed region)
+        if dist is not None and shard:
+            dist.barrier()                        # the ranks of one graph enter the step together
         eng.record(0)
         for first, cnt in sched:
             eng.divide_rounds(first, cnt)
@@ -304,6 +367,8 @@ def bench_ours(args, wl, rank, world, local_rank):
         eng.reset()
         eng.flush_l2()
         eng.sync()
+        if dist is not None and shard:
+            dist.barrier()
         t0 = time.perf_counter()
 
         def feed(i):
@@ -323,7 +388,6 @@ def bench_ours(args, wl, rank, world, local_rank):
                 feed(i + ahead)
             eng.decide_fame()
         lib, h = eng._lib, eng._h
-        import ctypes as C
         lib.sw_get_round(h, 0, N, out_round.ctypes.data_as(C.c_void_p))
         lib.sw_get_witness_flags(h, 0, N, out_wit.ctypes.data_as(C.c_void_p))
         lib.sw_get_famous(h, 0, N, out_fam.ctypes.data_as(C.c_void_p))
@@ -346,16 +410,19 @@ def bench_ours(args, wl, rank, world, local_rank):
         wall_ms = (time.perf_counter() - t0) * 1e3
         barrier()
     st1 = eng.stats()
-    check = (int(eng.rounds().astype(np.int64).sum()), int(eng.max_round), int(len(eng.consensus())))
+    got_round, got_wit, got_fam = eng.rounds(), eng.witness_flags(), eng.famous()
+    check = (int(got_round.astype(np.int64).sum()), int(eng.max_round), int(len(eng.consensus())))
 
-    # ---- find_order, timed separately (not part of the metric)
-    eng.rewind()
-    fo_ms0 = eng.stats()["ms_find_order"]
-    for first, cnt in sched:
-        eng.divide_rounds(first, cnt)
-        eng.find_order(eng.decide_fame())
-    fo_ms = eng.stats()["ms_find_order"] - fo_ms0
-    n_ordered = eng.n_transactions
+    # ---- find_order, timed separately (not part of the metric); every rank runs it (replicated)
+    fo_ms, n_ordered = None, None
+    if not args.no_find_order and M <= 256:
+        eng.rewind()
+        fo_ms0 = eng.stats()["ms_find_order"]
+        for first, cnt in sched:
+            eng.divide_rounds(first, cnt)
+            eng.find_order(eng.decide_fame())
+        fo_ms = eng.stats()["ms_find_order"] - fo_ms0
+        n_ordered = eng.n_transactions
 
     # ---- end-to-end leg from host buffers
     for _ in range(min(args.warmup, 2)):
@@ -366,10 +433,21 @@ def bench_ours(args, wl, rank, world, local_rank):
     for _ in range(e2e_steps):
         e2e_ms += step_e2e()
     st_e2e = eng.stats()              # sw_reset clears the counters: this is the last e2e step alone
+    e2e_same = bool(np.array_equal(out_round, got_round) and np.array_equal(out_wit, got_wit) and np.array_equal(out_fam, got_fam))
     barrier()
 
     dev_ms_max, e2e_ms_max, wall_ms_max = max_over_ranks([dev_ms, e2e_ms, wall_ms], dist, "cuda")
+    # sharded: every rank must hold identical results
+    same_on_all = True
+    if dist is not None and shard:
+        digest = torch.tensor([check[0], check[1], check[2], int(got_fam.astype(np.int64).sum()), int(got_wit.sum())],
+                              dtype=torch.int64, device="cuda")
+        lo, hi = digest.clone(), digest.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same_on_all = bool(torch.equal(lo, hi))
 
+    ok = True
     if rank == 0:
         peak, peak_src = load_peaks()
         launches = timed_launches[0]
@@ -378,27 +456,62 @@ def bench_ours(args, wl, rank, world, local_rank):
         n_div_launch = len(sched) * args.steps
         ms_cs = st1["ms_can_see"] - st0["ms_can_see"]
         ms_rk = st1["ms_rounds_kernel"] - st0["ms_rounds_kernel"]
-        impl = os.environ.get("SW_DIVIDE_IMPL", "5")
-        batch = impl not in ("3", "4")
-        bpe = rounds_bytes_per_event(M) if batch else algorithmic_bytes_per_event(M)
-        ms_dom = ms_rk if ms_rk > 0 else ms_div
-        achieved = (N * args.steps * bpe) / (ms_dom * 1e-3) / 1e9
+        wide = M > 64 or os.environ.get("SW_FORCE_WIDE", "0") not in ("", "0")
+        rk_name = "k_rounds_wide" if wide else "k_rounds_batch"
+        dominant_cs = ms_cs > ms_rk
         cs_achieved = (N * args.steps * can_see_bytes_per_event(M)) / (ms_cs * 1e-3) / 1e9 if ms_cs > 0 else None
+        rk_achieved = (N * args.steps * rounds_bytes_per_event(M)) / (ms_rk * 1e-3) / 1e9 if ms_rk > 0 else None
         path_achieved = (N * args.steps * algorithmic_bytes_per_event(M)) / ((ms_div + ms_fame) * 1e-3) / 1e9
-        value = whole_job_rate(world, N, args.steps, dev_ms_max)
-        e2e_value = whole_job_rate(world, N, e2e_steps, e2e_ms_max)
-        # CPU baseline next to it: one pass of the oracle port on the box's host cores
-        n_cpu, s_cpu, fo_cpu = run_cpu_pass(tr, K, limit=None if N <= 1000000 else 1000000)
+        value = whole_job_rate(world, N, args.steps, dev_ms_max, shard)
+        e2e_value = whole_job_rate(world, N, e2e_steps, e2e_ms_max, shard)
+        # ---- parity + CPU baseline next to it: the oracle port on the box's host cores, in this run
+        if N * (M / 64.0) ** 2 <= 1.2e6:
+            n_cpu, s_cpu, fo_cpu, ores = run_cpu_pass(tr, K)
+            exp_wit = np.zeros(N, np.uint8)
+            wt = ores["witness_table"]
+            exp_wit[wt[wt >= 0]] = 1
+            par = {"scope": "all %d events, element-wise" % N,
+                   "round": bool(np.array_equal(ores["round"], got_round)),
+                   "witness": bool(np.array_equal(exp_wit, got_wit)),
+                   "famous": bool(np.array_equal(ores["famous"], got_fam))}
+            cpu_sample = "full trace (%d events)" % n_cpu
+        else:
+            npre = max(2000, min(N, int(30 * port_rate_guess(M))))
+            n_cpu, s_cpu, fo_cpu, ores = run_cpu_pass(tr, npre, limit=npre)
+            e2 = engine.Engine(M, npre, device=local_rank)
+            e2.append_trace(tr, 0, npre)
+            e2.divide_rounds(0, npre)
+            e2.decide_fame()
+            exp_wit = np.zeros(npre, np.uint8)
+            wt = ores["witness_table"]
+            exp_wit[wt[wt >= 0]] = 1
+            par = {"scope": "prefix of %d events as one chunk (the literal oracle is O(M^2) per event), element-wise; "
+                            "full length: identical on all ranks = %s" % (npre, same_on_all),
+                   "round": bool(np.array_equal(ores["round"], e2.rounds())),
+                   "witness": bool(np.array_equal(exp_wit, e2.witness_flags())),
+                   "famous": bool(np.array_equal(ores["famous"], e2.famous())),
+                   "can_see": bool(np.array_equal(ores["oracle_can_see"], e2.can_see())) if "oracle_can_see" in ores else None}
+            e2.close()
+            cpu_sample = "first %d events as one chunk" % n_cpu
+        par["e2e_results_equal_resident"] = e2e_same
+        par["identical_on_all_ranks"] = same_on_all
+        ok = all(v for k, v in par.items() if k not in ("scope", "can_see") and v is not None)
+        par["ok"] = ok
+        dom_ms = ms_cs if dominant_cs else ms_rk
+        dom_bpe = can_see_bytes_per_event(M) if dominant_cs else rounds_bytes_per_event(M)
+        dom_ach = cs_achieved if dominant_cs else rk_achieved
+        dom_name = "k_cs_pass<2> (can_see scan family k_cs_*)" if dominant_cs else rk_name
         line = {
             "metric": "events/sec divide_rounds+decide_fame", "value": value, "unit": "events/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if shard else "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(wl, world),
             "clocks": clk.summary(),
+            "parity": ok, "parity_detail": par,
             "e2e": {"value": e2e_value, "unit": "events/s",
                     # counted by the library from the copies it issued in the last step (event columns incl. the
-                    # derived seq/height columns; results + per-call scalars)
+                    # derived seq/height/stale columns; results + per-call scalars)
                     "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
                     "ms_per_step": e2e_ms_max / e2e_steps,
                     "kernel_ms_last_step": {"divide_rounds": st_e2e["ms_divide_rounds"], "can_see_scan": st_e2e["ms_can_see"],
@@ -408,46 +521,47 @@ def bench_ours(args, wl, rank, world, local_rank):
                             "and the can_see scan overlap the round kernels; then round/witness/famous of every event "
                             "back to pinned host"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm",
-                         "kernel": ("k_rounds_batch (round numbers of a chunk: one cooperative launch per divide_rounds "
-                                    "call, one grid-wide step per round)") if batch else
-                                   "k_divide_levels (level walker: can_see rows + rounds + witnesses)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ((ROUNDS_DRAM_BYTES_PER_LAUNCH if batch else WALKER_DRAM_BYTES_PER_LAUNCH)
-                                     if (M == 64 and K == 65536) else None),
+            "roofline": {"bound": "hbm", "kernel": dom_name,
+                         "achieved": dom_ach, "peak": peak, "unit": "GB/s", "frac": dom_ach / peak if dom_ach else None,
+                         "traffic": DRAM_BYTES_PER_LAUNCH.get((rk_name, M, K)) if not dominant_cs else None,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
                                            "(profiles/README.md)",
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_event": bpe, "events_per_launch": K,
-                         "ms_per_launch": ms_dom / n_div_launch,
-                         "note": ("latency-bound, not HBM-bound: the depth of the computation is the number of rounds "
-                                  "(one grid barrier pair per round, ~1449 rounds per 1M events at M=64); cycle "
-                                  "accounting in profiles/ and tools/rounds_cycles.py") if batch else
-                                 "latency/issue-bound: one CTA walks ~53.7k dependent levels per 1M events at M=64"},
+                         "algorithmic_bytes_per_event": dom_bpe, "events_per_launch": K,
+                         "ms_per_launch": dom_ms / n_div_launch,
+                         "note": "latency-bound, not HBM-bound: the depth of the computation is the number of rounds (one "
+                                 "grid-wide step per round at M <= 64, a few steps per round above); DESIGN.md section 5"},
             "roofline_can_see": None if cs_achieved is None else {
-                "bound": "hbm", "kernel": "k_cs_local<.,1> + k_cs_collect + k_cs_boundary + k_cs_local<.,2> (blocked max-plus scan)",
+                "bound": "hbm", "kernel": "k_cs_prep + k_cs_pass<1> + k_cs_heads + k_cs_check + k_cs_slow + k_cs_pass<2> "
+                                          "(column-tiled blocked max-plus scan)",
                 "achieved": cs_achieved, "peak": peak, "unit": "GB/s", "frac": cs_achieved / peak,
                 "algorithmic_bytes_per_event": can_see_bytes_per_event(M), "ms_per_step": ms_cs / args.steps,
                 "note": "the resident leg scans all appended events in the first divide_rounds call of a step (the "
                         "end-to-end leg scans chunk by chunk, beside the round kernel of the previous chunk)"},
+            "roofline_rounds": None if rk_achieved is None else {
+                "bound": "hbm", "kernel": rk_name, "achieved": rk_achieved, "peak": peak, "unit": "GB/s",
+                "frac": rk_achieved / peak, "algorithmic_bytes_per_event": rounds_bytes_per_event(M),
+                "ms_per_launch": ms_rk / n_div_launch},
             "roofline_path": {"bound": "hbm", "what": "all kernels of divide_rounds + decide_fame, SURVEY.md 8d B(M)",
                               "achieved": path_achieved, "peak": peak, "unit": "GB/s", "frac": path_achieved / peak,
                               "algorithmic_bytes_per_event": algorithmic_bytes_per_event(M)},
             "kernel_ms_per_step": {"divide_rounds": ms_div / args.steps, "decide_fame": ms_fame / args.steps,
                                    "can_see_scan": ms_cs / args.steps, "rounds_kernel": ms_rk / args.steps,
                                    "wall": wall_ms_max / args.steps},
-            "impl": {"divide": {"5": "5 (round batch)", "4": "4 (level walker)", "3": "3 (per-event flags)"}.get(impl, impl),
-                     "can_see": "scan" if batch else os.environ.get("SW_CANSEE_IMPL", "fused")},
+            "impl": {"rounds": rk_name, "can_see": "k_cs_* column-tiled scan"},
             "cpu_baseline": {"value": n_cpu / s_cpu, "unit": "events/s", "cores": 1, "kind": "port",
-                             "sample": "full trace (%d events), oracle/swirld_oracle.c single thread on a host with %d cpus"
-                                       % (n_cpu, os.cpu_count())},
-            "find_order": {"events_per_s": n_ordered / (fo_ms * 1e-3) if fo_ms > 0 else None, "ordered": int(n_ordered),
-                           "ms": fo_ms, "cpu_port_events_per_s": n_cpu / fo_cpu if fo_cpu > 0 else None},
+                             "sample": "%s, oracle/swirld_oracle.c single thread on a host with %d cpus" % (cpu_sample, os.cpu_count())},
+            "python_reference": python_reference_sample(tr, wl) if not args.no_python_reference else None,
+            "find_order": None if fo_ms is None else {
+                "events_per_s": n_ordered / (fo_ms * 1e-3) if fo_ms > 0 else None, "ordered": int(n_ordered),
+                "ms": fo_ms, "cpu_port_events_per_s": n_cpu / fo_cpu if fo_cpu > 0 else None},
             "checksum": {"round_sum": check[0], "max_round": check[1], "consensus_rounds": check[2]},
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
 
 
 def main():
@@ -458,6 +572,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--events", type=int, default=0, help="override the workload's event count")
+    ap.add_argument("--no-find-order", action="store_true")
+    ap.add_argument("--no-python-reference", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.events:

@@ -97,6 +97,7 @@ int sw_decide_fame(sw_engine *e, int32_t *new_c_out, int cap);
 int sw_find_order(sw_engine *e, const int32_t *new_c, int n);
 
 /* ---- views of the Node attributes (swirld.py:48-72) ---- */
+int sw_members(const sw_engine *e);           /* n (swirld.py:40) */
 int sw_n_events(const sw_engine *e);          /* len(hg) */
 int sw_n_divided(const sw_engine *e);         /* len(round) */
 int sw_max_round(sw_engine *e);               /* max(witnesses), -1 if none */
@@ -122,6 +123,24 @@ int sw_event_elapsed_ms(sw_engine *e, int slot_a, int slot_b, double *ms_out);
 
 /* Profiling aid: 16 cycle counters of k_rounds_batch (tools/rounds_cycles.py). */
 int sw_debug_counters(sw_engine *e, int64_t *out16, int clear);
+
+/* ---- ingest: the step of Node.sync between the wire and divide_rounds (swirld.py:129-136, utils.py:8-21) in C++.
+ * A batch of n events named by their 32-byte ids (BLAKE2b, swirld.py:95), parents given by id (32 zero bytes = none: a
+ * root).  Ids the engine knows already are skipped; the others are put in a parents-first order (iterative DFS over the
+ * batch; a cycle returns SW_E_ARG like toposort's ValueError), validated like sw_append validates (unknown parent,
+ * parent shape, fork -- such an event, and whatever depends on it, is skipped: index -1), appended by ONE sw_append in
+ * that order and entered in the engine's id -> index map.  index_out[i] = arrival index of input event i.  Returns
+ * the number of events appended.  Signature checks (Ed25519) stay with the caller (libsodium, out of scope). */
+int sw_ingest(sw_engine *e, int n, const uint8_t *ids, const uint8_t *p0_ids, const uint8_t *p1_ids,
+              const int32_t *creator, const double *t, const uint8_t *sig, int32_t *index_out);
+int sw_lookup(sw_engine *e, int n, const uint8_t *ids, int32_t *index_out);   /* id -> arrival index, -1 unknown */
+
+/* ---- checkpoint / resume (the reference keeps its state in memory only and uses pickle on the wire, swirld.py:129,160):
+ * the engine's whole state -- event columns, can_see table, rounds, witness / fame tables, order -- as one binary file
+ * of SoA sections.  sw_load builds a new engine from it (capacity_events 0 = the saved capacity; never less than the
+ * saved event count) that continues exactly where the saved one stopped: the same later calls give the same results. */
+int sw_save(sw_engine *e, const char *path);
+int sw_load(const char *path, int device, int capacity_events, sw_engine **out);
 
 /* ---- several GPUs of one box (one process per GPU), M > 64: ONE hashgraph, the P_r tests of every round step of
  * sw_divide_rounds sharded by member chain over the ranks; every rank writes its chains' first hits straight into

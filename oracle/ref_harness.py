@@ -26,6 +26,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("SWIRLD_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REF, "swirld.py")):
+    # the files __graft_entry__.build() staged (git-ignored; they travel to the GPU box with gpurun)
+    REF = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
 
 
 def reference_available() -> bool:

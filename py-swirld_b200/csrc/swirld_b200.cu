@@ -7,6 +7,7 @@
 #include "swirld_cansee.cuh"
 #include "swirld_rounds.cuh"
 #include "swirld_wide.cuh"
+#include "swirld_stream.cuh"
 
 #include <cstdlib>
 #include "../../include/swirld_b200.h"
@@ -15,12 +16,18 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <array>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
 
 std::string g_create_error;
+
+// 32-byte event ids (BLAKE2b, swirld.py:95) -> arrival index
+using Id32 = std::array<uint64_t, 4>;
+struct Id32Hash { size_t operator()(const Id32 &k) const { return (size_t)(k[0] ^ (k[1] * 0x9E3779B97F4A7C15ull)); } };
 
 struct TimedSpan { cudaEvent_t a, b; int cat; };
 
@@ -58,7 +65,7 @@ struct sw_engine {
     // can_see scan scratch (swirld_cansee.cuh)
     int4 *d_cs_meta = nullptr;
     uint8_t *d_cs_wr = nullptr, *d_cs_xb = nullptr, *d_cs_sflag = nullptr;
-    int32_t *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_carry = nullptr, *d_cs_slow = nullptr, *d_cs_slowcnt = nullptr;
+    int32_t *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_carry = nullptr, *d_cs_slow = nullptr, *d_cs_slowcnt = nullptr, *d_cs_xlist = nullptr;
     int cs_min_B = 256;           // smallest block length the scan uses (sizes the per-block scratch)
     double *d_t = nullptr;
     uint8_t *d_sig = nullptr;
@@ -91,12 +98,19 @@ struct sw_engine {
     int seg_cap = 0;
     void *d_flush = nullptr;
     size_t flush_bytes = 0;
+    // small appends (the reference's cadence: one sync per call): one packed copy instead of eight
+    static constexpr int STAGE_SLOTS = 8, STAGE_EVENTS = 64;
+    uint8_t *h_stage = nullptr, *d_stage = nullptr;
+    cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr};
+    int stage_next = 0;
+    int stream_n = 16;            // divide_rounds calls of at most this many events take the one-launch path (SW_STREAM_N)
     int32_t *h_scal = nullptr;    // pinned
     int32_t *h_newc = nullptr;    // pinned, Rcap
     cudaStream_t stream = nullptr;
     cudaEvent_t user_ev[16] = {nullptr};
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> pool;
+    std::unordered_map<Id32, int32_t, Id32Hash> ids;     // sw_ingest: event id -> arrival index
     sw_stats_t stats{};
     std::string err;
 };
@@ -231,7 +245,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     C.M = M; C.first = first; C.n = n;
     C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.stale = e->d_stale; C.row = e->d_row;
     C.meta = e->d_cs_meta; C.wr = e->d_cs_wr; C.xb = e->d_cs_xb; C.last = e->d_cs_last; C.Qtab = e->d_cs_Q;
-    C.carry = e->d_cs_carry; C.slow_list = e->d_cs_slow; C.slow_cnt = e->d_cs_slowcnt; C.sflag = e->d_cs_sflag;
+    C.carry = e->d_cs_carry; C.slow_list = e->d_cs_slow; C.slow_cnt = e->d_cs_slowcnt; C.sflag = e->d_cs_sflag; C.xlist = e->d_cs_xlist;
     cudaEvent_t a = get_event(e), b = get_event(e);
     int small_n = 24;
     if (const char *v = getenv("SW_CS_SMALL")) small_n = atoi(v);
@@ -254,22 +268,28 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     C.first_al = first & ~3;
     C.nb = (first + n <= C.first_al + B) ? 1 : 1 + (first + n - (C.first_al + B) + B - 1) / B;
     if (C.nb > 1 && first + n - (C.first_al + (C.nb - 1) * B) < 3 * B / 4) C.nb--;     // a short tail joins the block before it
-    const int ntiles = (M + CS_CT - 1) / CS_CT;
-    const size_t smem = (size_t)M * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
+    // columns per tile: 32 (one warp = one 128-byte row segment), fewer when the (block, tile) pairs would not even
+    // put one warp on every scheduler -- the walk is a latency chain, narrower tiles buy parallel chains
+    int CT = 32;
+    while (CT > 8 && (long long)C.nb * ((M + CT - 1) / CT) < 4LL * e->n_sm) CT >>= 1;
+    if (const char *v = getenv("SW_CS_CT")) { const int x = atoi(v); if (x == 8 || x == 16 || x == 32) CT = x; }
+    C.CT = CT;
+    const int ntiles = (M + CT - 1) / CT;
+    const size_t smem = (size_t)M * CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
     const int pblocks = std::max(1, std::min(8 * e->n_sm, (n + 255) / 256));
     k_fill_i32<<<std::max(1, std::min(256, (int)(((size_t)C.nb * M + 255) / 256))), 256, 0, st>>>(e->d_cs_last, -1, (size_t)C.nb * M);
     if (C.nb > 1) {
         CK(cudaMemsetAsync(e->d_cs_wr + first, 0, (size_t)n, st));
-        CK(cudaMemsetAsync(e->d_cs_xb + first, 0, (size_t)n, st));
+        CK(cudaMemsetAsync(e->d_cs_xb + (first & ~3), 0, (size_t)(n + (first & 3)), st));
         CK(cudaMemsetAsync(e->d_cs_sflag + first, 0, (size_t)n, st));
-        CK(cudaMemsetAsync(e->d_cs_slowcnt, 0, sizeof(int32_t) * 2, st));
+        CK(cudaMemsetAsync(e->d_cs_slowcnt, 0, sizeof(int32_t) * 4, st));
     }
     cudaEventRecord(a, st);
     k_cs_prep<<<pblocks, 256, 0, st>>>(C);
     if (C.nb > 1) k_cs_pass<1><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
-    k_cs_heads<<<(M + 127) / 128, 128, 0, st>>>(C);
+    k_cs_heads<<<std::max(1, std::min(2 * e->n_sm, (int)(((size_t)(C.nb + 1) * M + 255) / 256))), 256, 0, st>>>(C);
     if (C.nb > 1) {
-        k_cs_check<<<pblocks, 256, 0, st>>>(C);
+        k_cs_check<<<std::max(1, std::min(4 * e->n_sm, (int)(((size_t)C.nb * M + 7) / 8))), 256, 0, st>>>(C);
         k_cs_slow<<<1, CS_SLOW_WARPS * 32, (size_t)CS_SLOW_WARPS * M * sizeof(int), st>>>(C);
     }
     k_cs_pass<2><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
@@ -354,7 +374,7 @@ int divide_rounds_wide(sw_engine *e, int first, int n) {
     R.Wf = e->d_Wf; R.scw = e->d_scw; R.sctag = e->d_sctag; R.cev = e->d_cev;
     R.ccnt = e->d_rbmeta; R.cmin = e->d_rbmeta + M; R.coff = e->d_rbmeta + 2 * M; R.bar = reinterpret_cast<unsigned *>(e->d_rbmeta + 3 * M + 8);
     int32_t *wcnt = e->d_rbmeta + 3 * M + 9, *wlist = e->d_cev + e->cap;
-    R.ctot = e->d_rbtot; R.gchain = e->d_gchain; R.hitmin = e->d_hitmin;
+    R.ctot = e->d_rbtot; R.gchain = e->d_gchain; R.hitmin = e->d_hitmin; R.ticket = reinterpret_cast<unsigned *>(e->d_rbmeta + 3 * M + 12);
     R.stake = e->d_stake; R.tot2 = 2 * e->tot; R.unit = e->unit ? 1 : 0; R.scal = e->d_scal; R.dbg = e->d_dbg;
     R.rank = e->rank; R.nranks = e->nranks; R.xstep = e->d_xstep;
     for (int p = 0; p < e->nranks && p < 8; p++) {
@@ -463,7 +483,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         if (const char *v = getenv("SW_CS_B")) e->cs_min_B = std::max(64, std::min(e->cs_min_B, atoi(v)));
         const size_t nbmax = cap / e->cs_min_B + 3;
         CK(dalloc(&e->d_cs_meta, cap)); CK(dalloc(&e->d_cs_wr, cap)); CK(dalloc(&e->d_cs_xb, cap)); CK(dalloc(&e->d_cs_slow, cap + 4));
-        CK(dalloc(&e->d_cs_last, nbmax * M)); CK(dalloc(&e->d_cs_Q, (nbmax + 1) * M)); CK(dalloc(&e->d_cs_slowcnt, (size_t)4)); CK(dalloc(&e->d_cs_sflag, cap));
+        CK(dalloc(&e->d_cs_last, nbmax * M)); CK(dalloc(&e->d_cs_Q, (nbmax + 1) * M)); CK(dalloc(&e->d_cs_slowcnt, (size_t)4)); CK(dalloc(&e->d_cs_sflag, cap)); CK(dalloc(&e->d_cs_xlist, cap + 4));
         CK(dalloc(&e->d_cs_carry, MP));
         CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, 2 * cap)); /* + the witness list of the current chunk */
         CK(dalloc(&e->d_rbmeta, std::max<size_t>(256, 3 * MP + 64)));
@@ -490,6 +510,12 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(dalloc(&e->d_lastord, MP)); CK(dalloc(&e->d_tx, cap)); CK(dalloc(&e->d_idx, cap));
         CK(dalloc(&e->d_batch_ev, cap)); CK(dalloc(&e->d_batch_seg, cap)); CK(dalloc(&e->d_perm, 2 * cap));
         CK(dalloc(&e->d_ts, cap)); CK(dalloc(&e->d_key, cap * 8));
+        const size_t slot = (unpack_bytes(sw_engine::STAGE_EVENTS) + 255) & ~(size_t)255;
+        CK(cudaMallocHost((void **)&e->h_stage, slot * sw_engine::STAGE_SLOTS));
+        CK(cudaMalloc((void **)&e->d_stage, slot * sw_engine::STAGE_SLOTS));
+        for (auto &ev : e->stage_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (const char *v = getenv("SW_STREAM_N")) e->stream_n = std::max(0, std::min(1024, atoi(v)));
+        CK(cudaFuncSetAttribute(k_stream_divide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
         CK(cudaMallocHost((void **)&e->h_scal, sizeof(int32_t) * SC_COUNT));
         CK(cudaMallocHost((void **)&e->h_newc, sizeof(int32_t) * e->Rcap));
         CK(cudaMemcpyAsync(e->d_stake, e->h_stake.data(), sizeof(i64) * M, cudaMemcpyHostToDevice, e->stream));
@@ -515,9 +541,12 @@ void sw_destroy(sw_engine *e) {
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
     if (e->scan_ev) cudaEventDestroy(e->scan_ev);
+    for (auto ev : e->stage_ev) if (ev) cudaEventDestroy(ev);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->d_stage) cudaFree(e->d_stage);
     for (int p = 0; p < 8; p++) if (e->x_peer[p] && e->x_peer[p] != e->d_xbuf) cudaIpcCloseMemHandle(e->x_peer[p]);
     void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_carry,
-                    e->d_cs_meta, e->d_cs_wr, e->d_cs_xb, e->d_cs_sflag, e->d_cs_slow, e->d_cs_slowcnt, e->d_stale, e->d_coin, e->d_dbg, e->d_height,
+                    e->d_cs_meta, e->d_cs_wr, e->d_cs_xb, e->d_cs_sflag, e->d_cs_xlist, e->d_cs_slow, e->d_cs_slowcnt, e->d_stale, e->d_coin, e->d_dbg, e->d_height,
                     e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_SM,
                     e->d_scw, e->d_sctag, e->d_SMw, e->d_Sw, e->d_hitmin, e->d_xbuf, e->d_xstep,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_famous, e->d_consensus,
@@ -542,6 +571,7 @@ int sw_reset(sw_engine *e) {
     CK(cudaStreamSynchronize(e->stream));
     fold_spans(e);
     e->h_creator.clear();
+    e->ids.clear();
     int rc = reset_state(e);
     memset(&e->stats, 0, sizeof e->stats);
     return rc;
@@ -613,14 +643,36 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
     // The copies go to their own stream: they touch only the new rows, so they overlap the kernels of
     // earlier chunks still running on the compute stream; later compute work waits for them.
     cudaStream_t cs = e->copy_stream;
-    CK(cudaMemcpyAsync(e->d_p0 + base, p0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(e->d_p1 + base, p1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(e->d_creator + base, creator, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(e->d_t + base, t, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(e->d_sig + (size_t)base * 64, sig, (size_t)64 * n, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(e->d_seq + base, e->h_seq + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(e->d_height + base, e->h_height + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
-    CK(cudaMemcpyAsync(e->d_stale + base, e->h_stale + base, (size_t)n, cudaMemcpyHostToDevice, cs));
+    if (n <= sw_engine::STAGE_EVENTS) {
+        // a handful of events: pack the eight columns into one pinned block, one copy, one scatter kernel
+        const size_t slot = (unpack_bytes(sw_engine::STAGE_EVENTS) + 255) & ~(size_t)255;
+        const int si = e->stage_next;
+        e->stage_next = (si + 1) % sw_engine::STAGE_SLOTS;
+        CK(cudaEventSynchronize(e->stage_ev[si]));                       // (the copy that used this slot eight appends ago)
+        uint8_t *hs = e->h_stage + slot * si, *ds = e->d_stage + slot * si;
+        int32_t *ints = reinterpret_cast<int32_t *>(hs);
+        memcpy(ints, p0, sizeof(int32_t) * n); memcpy(ints + n, p1, sizeof(int32_t) * n); memcpy(ints + 2 * n, creator, sizeof(int32_t) * n);
+        memcpy(ints + 3 * n, e->h_seq + base, sizeof(int32_t) * n); memcpy(ints + 4 * n, e->h_height + base, sizeof(int32_t) * n);
+        uint8_t *pt = hs + unpack_off_t(n);
+        memcpy(pt, t, sizeof(double) * n); memcpy(pt + (size_t)8 * n, sig, (size_t)64 * n); memcpy(pt + (size_t)72 * n, e->h_stale + base, (size_t)n);
+        CK(cudaMemcpyAsync(ds, hs, unpack_bytes(n), cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(e->stage_ev[si], cs));
+        UnpackParams U{};
+        U.base = base; U.n = n; U.stage = ds; U.p0 = e->d_p0; U.p1 = e->d_p1; U.creator = e->d_creator; U.seq = e->d_seq;
+        U.height = e->d_height; U.t = e->d_t; U.sig = e->d_sig; U.stale = e->d_stale;
+        k_unpack<<<1, 256, 0, cs>>>(U);
+        CK(cudaGetLastError());
+        e->stats.kernel_launches += 1;
+    } else {
+        CK(cudaMemcpyAsync(e->d_p0 + base, p0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(e->d_p1 + base, p1, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(e->d_creator + base, creator, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(e->d_t + base, t, sizeof(double) * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(e->d_sig + (size_t)base * 64, sig, (size_t)64 * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(e->d_seq + base, e->h_seq + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(e->d_height + base, e->h_height + base, sizeof(int32_t) * n, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(e->d_stale + base, e->h_stale + base, (size_t)n, cudaMemcpyHostToDevice, cs));
+    }
     // rows are up to date and the batch is big: scan it now, beside the kernels of the previous chunk
     const bool eager = e->n_rowed == base && n >= 4096;
     e->stats.h2d_bytes += (i64)n * (5 * 4 + 1 + 8 + 64);
@@ -644,6 +696,32 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     if (first != e->n_divided) return fail(e, SW_E_ARG, "divide_rounds: first=%d but %d events are divided (events must arrive in order)", first, e->n_divided);
     if (first + n > e->n_events) return fail(e, SW_E_KEY, "divide_rounds: events [%d,%d) not appended", first, first + n);
     CK(cudaSetDevice(e->device));
+    if (n <= e->stream_n && e->n_rowed == first) {
+        // the reference's own cadence (one sync per call): the whole of divide_rounds in ONE launch (swirld_stream.cuh)
+        if (wait_appends(e, first + n) < 0) return SW_E_CUDA;
+        const int M = e->M;
+        StreamParams S{};
+        S.M = M; S.first = first; S.n = n; S.Rcap = e->Rcap; S.NJ = e->NJ;
+        S.p0 = e->d_p0; S.p1 = e->d_p1; S.creator = e->d_creator; S.seq = e->d_seq; S.row = e->d_row; S.round = e->d_round;
+        S.wit = e->d_wit; S.W = e->d_W; S.Wf = e->d_Wf; S.SM = e->d_SM; S.S = e->d_S; S.SMw = e->d_SMw; S.Sw = e->d_Sw;
+        S.coin = e->d_coin; S.sig = e->d_sig; S.stake = e->d_stake; S.tot2 = 2 * e->tot; S.scal = e->d_scal;
+        S.ctot = e->d_rbtot; S.gchain = e->d_gchain; S.carry = e->d_cs_carry; S.ring = RB_RING;
+        const int threads = std::min(1024, std::max(32, (M + 31) / 32 * 32));
+        const size_t smem = (size_t)M * 8 + 32 * 8 + (size_t)3 * M * 4 + 32 * 4;
+        {
+            Span sp(e, 0);
+            if (e->wide) k_stream_divide<true><<<1, threads, smem, e->stream>>>(S);
+            else k_stream_divide<false><<<1, threads, smem, e->stream>>>(S);
+            CK(cudaGetLastError());
+        }
+        e->n_rowed = first + n;
+        CK(cudaEventRecord(e->scan_ev, e->stream));         // (it wrote can_see rows and the carry heads on the compute stream)
+        e->scan_ev_set = true;
+        e->stats.kernel_launches += 1;
+        e->stats.events_divided += n;
+        e->n_divided += n;
+        return SW_OK;
+    }
     if (first + n > e->n_rowed) {
         // rows are behind (small appends, or after sw_rewind): scan everything appended so far, here -- after the
         // copies of EVERY appended batch (the scan reads the columns of all of them)
@@ -772,6 +850,7 @@ int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
     return nbatch;
 }
 
+int sw_members(const sw_engine *e) { return e ? e->M : SW_E_ARG; }
 int sw_n_events(const sw_engine *e) { return e ? e->n_events : SW_E_ARG; }
 int sw_n_divided(const sw_engine *e) { return e ? e->n_divided : SW_E_ARG; }
 int sw_n_transactions(const sw_engine *e) { return e ? e->n_tx : SW_E_ARG; }
@@ -863,6 +942,247 @@ int sw_flush_l2(sw_engine *e, int64_t bytes) {
         e->flush_bytes = (size_t)bytes;
     }
     CK(cudaMemsetAsync(e->d_flush, 0x5a, (size_t)bytes, e->stream));
+    return SW_OK;
+}
+
+// ---- ingest: what Node.sync does between the wire and divide_rounds (swirld.py:129-136, utils.py:8-21), natively
+int sw_ingest(sw_engine *e, int n, const uint8_t *ids, const uint8_t *p0_ids, const uint8_t *p1_ids,
+              const int32_t *creator, const double *t, const uint8_t *sig, int32_t *index_out) {
+    if (!e || n < 0 || (n > 0 && (!ids || !p0_ids || !p1_ids || !creator || !t || !sig || !index_out))) return fail(e, SW_E_ARG, "bad argument");
+    auto key = [](const uint8_t *p) { Id32 k; memcpy(k.data(), p, 32); return k; };
+    const Id32 zero{};
+    // 1. which events are new, and where each new id sits in the batch
+    std::unordered_map<Id32, int, Id32Hash> inbatch;
+    inbatch.reserve((size_t)n * 2);
+    for (int i = 0; i < n; i++) {
+        const Id32 k = key(ids + (size_t)32 * i);
+        auto it = e->ids.find(k);
+        if (it != e->ids.end()) index_out[i] = it->second;
+        else { index_out[i] = -1; inbatch.emplace(k, i); }       // (a duplicate id in the batch: the first one counts)
+    }
+    // 2. parents-first order of the new ones (iterative DFS; the edges are the parents that are in the batch)
+    std::vector<int> order, state(n, 0);                           // 0 unseen, 1 on the stack, 2 done
+    order.reserve(inbatch.size());
+    std::vector<std::pair<int, int>> stack;
+    auto parent_in_batch = [&](int i, int which) -> int {
+        const Id32 k = key((which ? p1_ids : p0_ids) + (size_t)32 * i);
+        if (k == zero) return -1;
+        auto it = inbatch.find(k);
+        return it == inbatch.end() ? -1 : it->second;
+    };
+    for (int r = 0; r < n; r++) {
+        if (index_out[r] >= 0 || state[r] || inbatch.find(key(ids + (size_t)32 * r))->second != r) continue;
+        stack.push_back({r, 0});
+        state[r] = 1;
+        while (!stack.empty()) {
+            auto &[u, next] = stack.back();
+            if (next < 2) {
+                const int v = parent_in_batch(u, next++);
+                if (v < 0 || state[v] == 2) continue;
+                if (state[v] == 1) return fail(e, SW_E_ARG, "sw_ingest: the batch is not a DAG (utils.py:13)");
+                state[v] = 1;
+                stack.push_back({v, 0});
+            } else { state[u] = 2; order.push_back(u); stack.pop_back(); }
+        }
+    }
+    // 3. validate in that order against a scratch copy of the chain heads; what fails (and what hangs below it) is skipped
+    std::vector<int32_t> head(e->h_head), bidx(n, -1), bcreator;
+    std::vector<int32_t> c_p0, c_p1, c_cr, src;
+    std::vector<double> c_t;
+    int next_index = e->n_events;
+    auto resolve = [&](int i, int which, int &out) -> bool {        // parent id -> arrival index (-1: no parent)
+        const Id32 k = key((which ? p1_ids : p0_ids) + (size_t)32 * i);
+        if (k == zero) { out = -1; return true; }
+        auto g = e->ids.find(k);
+        if (g != e->ids.end()) { out = g->second; return true; }
+        auto b = inbatch.find(k);
+        if (b != inbatch.end() && bidx[b->second] >= 0) { out = bidx[b->second]; return true; }
+        return false;
+    };
+    auto creator_of = [&](int idx) { return idx < e->n_events ? e->h_creator[idx] : bcreator[idx - e->n_events]; };
+    for (int i : order) {
+        const int c = creator[i];
+        int a, b;
+        if (c < 0 || c >= e->M || !resolve(i, 0, a) || !resolve(i, 1, b)) continue;
+        if (a < 0 && b < 0) { if (head[c] >= 0) continue; }                         // a second root: fork
+        else if (a < 0 || b < 0 || creator_of(a) != c || creator_of(b) == c || head[c] != a) continue;   // swirld.py:104-108 + fork-free
+        if (next_index >= e->cap) return fail(e, SW_E_CAPACITY, "capacity_events=%d exceeded", e->cap);
+        bidx[i] = next_index++;
+        head[c] = bidx[i];
+        bcreator.push_back(c);
+        c_p0.push_back(a); c_p1.push_back(b); c_cr.push_back(c); c_t.push_back(t[i]); src.push_back(i);
+    }
+    // 4. one sw_append for the accepted events, then the ids
+    const int m = (int)src.size();
+    if (m > 0) {
+        std::vector<uint8_t> c_sig((size_t)64 * m);
+        for (int j = 0; j < m; j++) memcpy(c_sig.data() + (size_t)64 * j, sig + (size_t)64 * src[j], 64);
+        int rc = sw_append(e, m, c_p0.data(), c_p1.data(), c_cr.data(), c_t.data(), c_sig.data());
+        if (rc < 0) return rc;
+        // (pageable sources: the copies are staged before sw_append returns, the vectors may go)
+        CK(cudaStreamSynchronize(e->copy_stream));
+        for (int j = 0; j < m; j++) e->ids.emplace(key(ids + (size_t)32 * src[j]), bidx[src[j]]);
+    }
+    for (int i = 0; i < n; i++)
+        if (index_out[i] < 0) { auto it = e->ids.find(key(ids + (size_t)32 * i)); index_out[i] = it == e->ids.end() ? -1 : it->second; }
+    return m;
+}
+
+int sw_lookup(sw_engine *e, int n, const uint8_t *ids, int32_t *index_out) {
+    if (!e || n < 0 || (n > 0 && (!ids || !index_out))) return fail(e, SW_E_ARG, "bad argument");
+    for (int i = 0; i < n; i++) {
+        Id32 k;
+        memcpy(k.data(), ids + (size_t)32 * i, 32);
+        auto it = e->ids.find(k);
+        index_out[i] = it == e->ids.end() ? -1 : it->second;
+    }
+    return SW_OK;
+}
+
+// ---- checkpoint / resume: the engine's whole state as one binary file (sections of SoA columns)
+namespace {
+struct CkptHeader {
+    char magic[8];
+    int32_t version, M, cap, C, Rcap, wide, NJ, n_events, n_divided, n_tx, n_rowed, rounds;
+    uint32_t rb_epoch, n_ids;
+};
+const char CKPT_MAGIC[8] = {'S', 'W', 'B', '2', 'C', 'K', 'P', 'T'};
+
+bool put_host(FILE *f, const void *p, size_t bytes) {
+    uint64_t nb = bytes;
+    return fwrite(&nb, 8, 1, f) == 1 && (bytes == 0 || fwrite(p, 1, bytes, f) == bytes);
+}
+bool put_dev(sw_engine *e, FILE *f, const void *d, size_t bytes, std::vector<char> &tmp) {
+    uint64_t nb = bytes;
+    if (fwrite(&nb, 8, 1, f) != 1) return false;
+    const size_t CH = (size_t)64 << 20;
+    for (size_t o = 0; o < bytes; o += CH) {
+        const size_t k = std::min(CH, bytes - o);
+        tmp.resize(k);
+        if (cudaMemcpyAsync(tmp.data(), (const char *)d + o, k, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) return false;
+        if (fwrite(tmp.data(), 1, k, f) != k) return false;
+    }
+    return true;
+}
+bool get_host(FILE *f, void *p, size_t bytes) {
+    uint64_t nb = 0;
+    return fread(&nb, 8, 1, f) == 1 && nb == bytes && (bytes == 0 || fread(p, 1, bytes, f) == bytes);
+}
+bool get_dev(sw_engine *e, FILE *f, void *d, size_t bytes, std::vector<char> &tmp) {
+    uint64_t nb = 0;
+    if (fread(&nb, 8, 1, f) != 1 || nb != bytes) return false;
+    const size_t CH = (size_t)64 << 20;
+    for (size_t o = 0; o < bytes; o += CH) {
+        const size_t k = std::min(CH, bytes - o);
+        tmp.resize(k);
+        if (fread(tmp.data(), 1, k, f) != k) return false;
+        if (cudaMemcpyAsync((char *)d + o, tmp.data(), k, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) return false;
+    }
+    return true;
+}
+}  // namespace
+
+int sw_save(sw_engine *e, const char *path) {
+    if (!e || !path) return fail(e, SW_E_ARG, "bad argument");
+    if (e->nranks > 1) return fail(e, SW_E_UNSUPPORTED, "sw_save: checkpoint one rank of a multi-GPU engine is not supported");
+    int rc = sw_sync(e);
+    if (rc < 0) return rc;
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(e, SW_E_ARG, "sw_save: cannot open %s", path);
+    const int M = e->M, n = e->n_events, nd = e->n_divided, nr = e->n_rowed;
+    const int R = std::min(e->Rcap, e->h_scal[SC_MAX_ROUND] + 2);
+    CkptHeader H{};
+    memcpy(H.magic, CKPT_MAGIC, 8);
+    H.version = 1; H.M = M; H.cap = e->cap; H.C = e->C; H.Rcap = e->Rcap; H.wide = e->wide ? 1 : 0; H.NJ = e->NJ;
+    H.n_events = n; H.n_divided = nd; H.n_tx = e->n_tx; H.n_rowed = nr; H.rounds = R; H.rb_epoch = e->rb_epoch;
+    H.n_ids = (uint32_t)e->ids.size();
+    std::vector<uint8_t> idrec((size_t)36 * e->ids.size());
+    { size_t o = 0; for (auto &kv : e->ids) { memcpy(&idrec[o], kv.first.data(), 32); memcpy(&idrec[o + 32], &kv.second, 4); o += 36; } }
+    std::vector<char> tmp;
+    const size_t RM = (size_t)R * M;
+    bool ok = fwrite(&H, sizeof H, 1, f) == 1 && put_host(f, e->h_stake.data(), sizeof(i64) * M)
+        && put_host(f, e->h_creator.data(), sizeof(int32_t) * n) && put_host(f, e->h_head.data(), sizeof(int32_t) * M)
+        && put_host(f, e->h_count.data(), sizeof(int32_t) * M) && put_host(f, e->h_height, sizeof(int32_t) * n)
+        && put_host(f, e->h_seq, sizeof(int32_t) * n) && put_host(f, e->h_stale, (size_t)n)
+        && put_dev(e, f, e->d_p0, sizeof(int32_t) * n, tmp) && put_dev(e, f, e->d_p1, sizeof(int32_t) * n, tmp)
+        && put_dev(e, f, e->d_creator, sizeof(int32_t) * n, tmp) && put_dev(e, f, e->d_t, sizeof(double) * n, tmp)
+        && put_dev(e, f, e->d_sig, (size_t)64 * n, tmp)
+        && put_dev(e, f, e->d_row, sizeof(int32_t) * (size_t)nr * M, tmp)
+        && put_dev(e, f, e->d_round, sizeof(int32_t) * nd, tmp) && put_dev(e, f, e->d_wit, (size_t)nd, tmp)
+        && (e->wide ? put_dev(e, f, e->d_SMw, sizeof(unsigned) * (size_t)nd * e->NJ, tmp) : put_dev(e, f, e->d_SM, sizeof(u64) * nd, tmp))
+        && put_dev(e, f, e->d_famous_ev, (size_t)n, tmp) && put_dev(e, f, e->d_idx, sizeof(int32_t) * n, tmp)
+        && put_dev(e, f, e->d_tx, sizeof(int32_t) * e->n_tx, tmp)
+        && put_dev(e, f, e->d_W, sizeof(int32_t) * RM, tmp) && put_dev(e, f, e->d_Wf, sizeof(int32_t) * RM, tmp)
+        && put_dev(e, f, e->d_famous, RM, tmp) && put_dev(e, f, e->d_coin, RM, tmp)
+        && (e->wide ? put_dev(e, f, e->d_Sw, sizeof(unsigned) * RM * e->NJ, tmp) : put_dev(e, f, e->d_S, sizeof(u64) * RM, tmp))
+        && put_dev(e, f, e->d_consensus, (size_t)R, tmp)
+        && put_dev(e, f, e->d_lastord, sizeof(int32_t) * M, tmp) && put_dev(e, f, e->d_cs_carry, sizeof(int32_t) * M, tmp)
+        && put_dev(e, f, e->d_rbtot, sizeof(int32_t) * M, tmp) && put_dev(e, f, e->d_gchain, sizeof(int32_t) * (size_t)M * RB_RING, tmp)
+        && put_dev(e, f, e->d_scal, sizeof(int32_t) * SC_COUNT, tmp) && put_host(f, idrec.data(), idrec.size());
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(e, SW_E_ARG, "sw_save: write to %s failed", path);
+    return SW_OK;
+}
+
+int sw_load(const char *path, int device, int capacity_events, sw_engine **out) {
+    sw_engine *e = nullptr;
+    if (!path || !out) return fail(e, SW_E_ARG, "bad argument");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(e, SW_E_ARG, "sw_load: cannot open %s", path);
+    CkptHeader H{};
+    if (fread(&H, sizeof H, 1, f) != 1 || memcmp(H.magic, CKPT_MAGIC, 8) != 0 || H.version != 1 || H.M < 1 || H.M > SW_MAX_MEMBERS) {
+        fclose(f);
+        return fail(e, SW_E_ARG, "sw_load: %s is not a swirld_b200 checkpoint", path);
+    }
+    std::vector<i64> stake(H.M);
+    if (!get_host(f, stake.data(), sizeof(i64) * H.M)) { fclose(f); return fail(e, SW_E_ARG, "sw_load: truncated file"); }
+    const int cap = std::max(capacity_events > 0 ? capacity_events : H.cap, H.n_events);
+    // the saved engine's path (wide or not) is restored whatever SW_FORCE_WIDE says now
+    setenv("SW_FORCE_WIDE", H.wide ? "1" : "0", 1);
+    int rc = sw_create(H.M, cap, reinterpret_cast<const int64_t *>(stake.data()), H.C, device, &e);
+    unsetenv("SW_FORCE_WIDE");
+    if (rc < 0) { fclose(f); return rc; }
+    const int M = H.M, n = H.n_events, nd = H.n_divided, nr = H.n_rowed, R = H.rounds;
+    if (R > e->Rcap || (int)e->wide != H.wide || e->NJ != H.NJ) { fclose(f); sw_destroy(e); return fail(nullptr, SW_E_ARG, "sw_load: checkpoint does not fit the engine"); }
+    std::vector<char> tmp;
+    const size_t RM = (size_t)R * M;
+    e->h_creator.resize(n);
+    bool ok = get_host(f, e->h_creator.data(), sizeof(int32_t) * n) && get_host(f, e->h_head.data(), sizeof(int32_t) * M)
+        && get_host(f, e->h_count.data(), sizeof(int32_t) * M) && get_host(f, e->h_height, sizeof(int32_t) * n)
+        && get_host(f, e->h_seq, sizeof(int32_t) * n) && get_host(f, e->h_stale, (size_t)n)
+        && get_dev(e, f, e->d_p0, sizeof(int32_t) * n, tmp) && get_dev(e, f, e->d_p1, sizeof(int32_t) * n, tmp)
+        && get_dev(e, f, e->d_creator, sizeof(int32_t) * n, tmp) && get_dev(e, f, e->d_t, sizeof(double) * n, tmp)
+        && get_dev(e, f, e->d_sig, (size_t)64 * n, tmp)
+        && get_dev(e, f, e->d_row, sizeof(int32_t) * (size_t)nr * M, tmp)
+        && get_dev(e, f, e->d_round, sizeof(int32_t) * nd, tmp) && get_dev(e, f, e->d_wit, (size_t)nd, tmp)
+        && (e->wide ? get_dev(e, f, e->d_SMw, sizeof(unsigned) * (size_t)nd * e->NJ, tmp) : get_dev(e, f, e->d_SM, sizeof(u64) * nd, tmp))
+        && get_dev(e, f, e->d_famous_ev, (size_t)n, tmp) && get_dev(e, f, e->d_idx, sizeof(int32_t) * n, tmp)
+        && get_dev(e, f, e->d_tx, sizeof(int32_t) * H.n_tx, tmp)
+        && get_dev(e, f, e->d_W, sizeof(int32_t) * RM, tmp) && get_dev(e, f, e->d_Wf, sizeof(int32_t) * RM, tmp)
+        && get_dev(e, f, e->d_famous, RM, tmp) && get_dev(e, f, e->d_coin, RM, tmp)
+        && (e->wide ? get_dev(e, f, e->d_Sw, sizeof(unsigned) * RM * e->NJ, tmp) : get_dev(e, f, e->d_S, sizeof(u64) * RM, tmp))
+        && get_dev(e, f, e->d_consensus, (size_t)R, tmp)
+        && get_dev(e, f, e->d_lastord, sizeof(int32_t) * M, tmp) && get_dev(e, f, e->d_cs_carry, sizeof(int32_t) * M, tmp)
+        && get_dev(e, f, e->d_rbtot, sizeof(int32_t) * M, tmp) && get_dev(e, f, e->d_gchain, sizeof(int32_t) * (size_t)M * RB_RING, tmp)
+        && get_dev(e, f, e->d_scal, sizeof(int32_t) * SC_COUNT, tmp);
+    if (ok) {
+        std::vector<uint8_t> idrec((size_t)36 * H.n_ids);
+        ok = get_host(f, idrec.data(), idrec.size());
+        for (size_t o = 0; ok && o < idrec.size(); o += 36) { Id32 k; int32_t v; memcpy(k.data(), &idrec[o], 32); memcpy(&v, &idrec[o + 32], 4); e->ids.emplace(k, v); }
+    }
+    fclose(f);
+    if (!ok) { sw_destroy(e); return fail(nullptr, SW_E_ARG, "sw_load: %s is truncated or does not match its header", path); }
+    // the derived columns live on the device too
+    bool ok2 = cudaMemcpy(e->d_seq, e->h_seq, sizeof(int32_t) * n, cudaMemcpyHostToDevice) == cudaSuccess
+        && cudaMemcpy(e->d_height, e->h_height, sizeof(int32_t) * n, cudaMemcpyHostToDevice) == cudaSuccess
+        && cudaMemcpy(e->d_stale, e->h_stale, (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok2) { sw_destroy(e); return fail(nullptr, SW_E_CUDA, "sw_load: device copy failed"); }
+    e->n_events = n; e->n_divided = nd; e->n_tx = H.n_tx; e->n_rowed = nr; e->rb_epoch = H.rb_epoch;
+    e->stats.events = n; e->stats.events_divided = nd;
+    *out = e;
     return SW_OK;
 }
 

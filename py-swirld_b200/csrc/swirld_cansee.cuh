@@ -31,6 +31,7 @@
 
 struct CsParams {
     int M, first, n, B, nb, first_al;   // events [first, first+n); block 0 = [first, first_al+B), block j = [first_al+jB, ..)
+    int CT;                     // columns per tile: 32, or 16 / 8 when there are too few (block, tile) pairs to fill the GPU
     const int32_t *p0, *p1, *creator;
     const uint8_t *stale;       // [cap] from sw_append: the other-parent is not its member's latest event
     int32_t *row;               // [cap][M]; rows < first are final
@@ -40,12 +41,13 @@ struct CsParams {
     int32_t *Qtab;              // [nb+1][M] head of member m at the start of block j
     int32_t *carry;             // [M] heads before `first` (in/out)
     int32_t *slow_list;         // [cap] the listed rows that failed the check (any order)
-    int32_t *slow_cnt;          // [2]: their count, rows still pending; zero on entry
+    int32_t *slow_cnt;          // [4]: slow rows, (unused), rows on xlist; zero on entry
+    int32_t *xlist;             // [cap] the rows a later block reads (each once)
     uint8_t *sflag;             // [cap] 0 final, 1 pending slow row, 2 finished by k_cs_slow, 3 finished in the running wave
 };
 
 #define CS_TILE 128
-#define CS_CT 32                // columns per tile = threads per CTA
+#define CS_CT 32                // threads per CTA (one warp); columns per tile = P.CT <= 32
 
 // (the last block takes whatever is left: a short tail block would fail the finality check often, so the host
 //  folds a tail shorter than 3B/4 into the block before it)
@@ -63,9 +65,15 @@ __global__ void __launch_bounds__(256) k_cs_prep(CsParams P) {
         const int st = (b >= 0 && P.stale[h]) ? 1 : 0;
         const int bh = cs_block_of(P, h);
         if (P.nb > 1) {
-            if (a >= P.first && cs_block_of(P, a) != bh) { P.wr[a] = 1; P.xb[a] = 1; }
+            auto mark = [&](int p) {                   // referenced from a later block: listed for the finality check, once
+                P.wr[p] = 1;
+                const unsigned sh = 8u * (p & 3);
+                const unsigned old = atomicOr(reinterpret_cast<unsigned *>(P.xb + (p & ~3)), 1u << sh);
+                if (!((old >> sh) & 1u)) P.xlist[atomicAdd(&P.slow_cnt[2], 1)] = p;
+            };
+            if (a >= P.first && cs_block_of(P, a) != bh) mark(a);
             if (b >= P.first) {
-                if (cs_block_of(P, b) != bh) { P.wr[b] = 1; P.xb[b] = 1; }
+                if (cs_block_of(P, b) != bh) mark(b);
                 else if (st) P.wr[b] = 1;
             }
             atomicMax(&P.last[(size_t)bh * P.M + c], h);
@@ -96,28 +104,35 @@ __global__ void __launch_bounds__(256) k_cs_prep(CsParams P) {
 template <int PASS>
 __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     extern __shared__ int cs_smem[];
-    int (*val)[CS_CT] = reinterpret_cast<int (*)[CS_CT]>(cs_smem);                 // [M][32]
-    int4 *meta = reinterpret_cast<int4 *>(cs_smem + (size_t)P.M * CS_CT);          // [CS_TILE]
+    const int CT = P.CT;
+    int4 *meta = reinterpret_cast<int4 *>(cs_smem);                                // [CS_TILE]
     uint8_t *wrt = reinterpret_cast<uint8_t *>(meta + CS_TILE);                    // [CS_TILE]
-    const int lane = threadIdx.x, M = P.M, blk = blockIdx.x;
-    const int c = blockIdx.y * CS_CT + lane;
-    const bool col = c < M;
+    int *valb = cs_smem + CS_TILE * 4 + CS_TILE / 4;                               // [M][CT]
+    const int tl = threadIdx.x, M = P.M, blk = blockIdx.x;
+    const int lane = tl & (CT - 1);                                                // lanes >= CT shadow lane % CT (their stores are off)
+    const int c = blockIdx.y * CT + lane;
+    const bool own = tl < CT;                                                      // (a shadow lane never stores)
+    const bool col = own && c < M;
+    if (PASS == 2 && blockIdx.x == 0 && blockIdx.y == 0)                           // the next launch's carry heads
+        for (int m = tl; m < M; m += CS_CT) P.carry[m] = P.Qtab[(size_t)P.nb * M + m];
+#define val(m) (valb + (size_t)(m) * CT)
     const int s = cs_start(P, blk), e = cs_end(P, blk);
     int32_t *rowc = P.row + (col ? c : 0);
     if (PASS == 1) {
-        for (int m = 0; m < M; m++) val[m][lane] = -1;
+        for (int m = 0; m < M; m++) if (own) val(m)[lane] = -1;
     } else {
         const int32_t *Q = P.Qtab + (size_t)blk * M;
 #pragma unroll 8
         for (int m = 0; m < M; m++) {
             const int q = Q[m];
-            val[m][lane] = (q >= 0 && col) ? rowc[(size_t)q * M] : -1;
+            const int v0 = (q >= 0 && col) ? rowc[(size_t)q * M] : -1;
+            if (own) val(m)[lane] = v0;
         }
     }
     for (int t0 = s; t0 < e; t0 += CS_TILE) {
         const int tn = min(CS_TILE, e - t0);
         __syncwarp();
-        for (int i = lane; i < tn; i += CS_CT) {
+        for (int i = tl; i < tn; i += CS_CT) {
             meta[i] = P.meta[t0 + i];
             if (PASS == 1) wrt[i] = P.wr[t0 + i];
         }
@@ -132,20 +147,20 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 const int c0 = m0.z & 0xffff, c1 = m1.z & 0xffff, c2 = m2.z & 0xffff, c3 = m3.z & 0xffff;
                 int x0, x1, x2, x3, y0, y1, y2, y3;
                 if (PASS == 1) {
-                    x0 = m0.x >= s ? val[c0][lane] : -1; x1 = m1.x >= s ? val[c1][lane] : -1;
-                    x2 = m2.x >= s ? val[c2][lane] : -1; x3 = m3.x >= s ? val[c3][lane] : -1;
-                    y0 = m0.y >= s ? val[m0.w][lane] : ((m0.y >= 0 && c == m0.w) ? m0.y : -1);
-                    y1 = m1.y >= s ? val[m1.w][lane] : ((m1.y >= 0 && c == m1.w) ? m1.y : -1);
-                    y2 = m2.y >= s ? val[m2.w][lane] : ((m2.y >= 0 && c == m2.w) ? m2.y : -1);
-                    y3 = m3.y >= s ? val[m3.w][lane] : ((m3.y >= 0 && c == m3.w) ? m3.y : -1);
+                    x0 = m0.x >= s ? val(c0)[lane] : -1; x1 = m1.x >= s ? val(c1)[lane] : -1;
+                    x2 = m2.x >= s ? val(c2)[lane] : -1; x3 = m3.x >= s ? val(c3)[lane] : -1;
+                    y0 = m0.y >= s ? val(m0.w)[lane] : ((m0.y >= 0 && c == m0.w) ? m0.y : -1);
+                    y1 = m1.y >= s ? val(m1.w)[lane] : ((m1.y >= 0 && c == m1.w) ? m1.y : -1);
+                    y2 = m2.y >= s ? val(m2.w)[lane] : ((m2.y >= 0 && c == m2.w) ? m2.y : -1);
+                    y3 = m3.y >= s ? val(m3.w)[lane] : ((m3.y >= 0 && c == m3.w) ? m3.y : -1);
                 } else {
-                    x0 = val[c0][lane]; x1 = val[c1][lane]; x2 = val[c2][lane]; x3 = val[c3][lane];
-                    y0 = m0.y >= 0 ? val[m0.w][lane] : -1; y1 = m1.y >= 0 ? val[m1.w][lane] : -1;
-                    y2 = m2.y >= 0 ? val[m2.w][lane] : -1; y3 = m3.y >= 0 ? val[m3.w][lane] : -1;
+                    x0 = val(c0)[lane]; x1 = val(c1)[lane]; x2 = val(c2)[lane]; x3 = val(c3)[lane];
+                    y0 = m0.y >= 0 ? val(m0.w)[lane] : -1; y1 = m1.y >= 0 ? val(m1.w)[lane] : -1;
+                    y2 = m2.y >= 0 ? val(m2.w)[lane] : -1; y3 = m3.y >= 0 ? val(m3.w)[lane] : -1;
                 }
                 const int v0 = c == c0 ? h : max(x0, y0), v1 = c == c1 ? h + 1 : max(x1, y1);
                 const int v2 = c == c2 ? h + 2 : max(x2, y2), v3 = c == c3 ? h + 3 : max(x3, y3);
-                val[c0][lane] = v0; val[c1][lane] = v1; val[c2][lane] = v2; val[c3][lane] = v3;
+                if (own) { val(c0)[lane] = v0; val(c1)[lane] = v1; val(c2)[lane] = v2; val(c3)[lane] = v3; }
                 if (PASS == 2) {
                     if (col) {
                         rowc[(size_t)h * M] = v0; rowc[(size_t)(h + 1) * M] = v1;
@@ -162,15 +177,15 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 const int a = m0.x, b = m0.y, cr = m0.z & 0xffff, st = (m0.z >> 16) & 1, cb = m0.w;
                 int x, y;
                 if (PASS == 1) {
-                    x = a >= s ? val[cr][lane] : -1;
-                    if (b >= s) y = st ? (col ? rowc[(size_t)b * M] : -1) : val[cb][lane];
+                    x = a >= s ? val(cr)[lane] : -1;
+                    if (b >= s) y = st ? (col ? rowc[(size_t)b * M] : -1) : val(cb)[lane];
                     else y = (b >= 0 && c == cb) ? b : -1;
                 } else {
-                    x = val[cr][lane];
-                    y = b < 0 ? -1 : (st ? (col ? rowc[(size_t)b * M] : -1) : val[cb][lane]);
+                    x = val(cr)[lane];
+                    y = b < 0 ? -1 : (st ? (col ? rowc[(size_t)b * M] : -1) : val(cb)[lane]);
                 }
                 const int v = c == cr ? h : max(x, y);
-                val[cr][lane] = v;
+                if (own) val(cr)[lane] = v;
                 if (col && (PASS == 2 || wrt[i])) rowc[(size_t)h * M] = v;
                 i += 1;
             }
@@ -183,57 +198,51 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
 #pragma unroll
             for (int u = 0; u < 8; u++) l[u] = m0 + u < M ? __ldg(L + m0 + u) : -1;
 #pragma unroll
-            for (int u = 0; u < 8; u++) if (l[u] >= 0) rowc[(size_t)l[u] * M] = val[m0 + u][lane];
+            for (int u = 0; u < 8; u++) if (l[u] >= 0) rowc[(size_t)l[u] * M] = val(m0 + u)[lane];
         }
     }
+#undef val
 }
 
-// heads at the start of every block (and after the range: the next launch's carry)
+// heads at the start of every block: Q[j][m] = member m's latest event below block j = its last event of the nearest
+// earlier block that has one (with B >= 16 M that is the block before, almost always), else the carry head.  Row nb is
+// the carry of the next launch (installed by k_cs_pass<2>).
 __global__ void k_cs_heads(CsParams P) {
-    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < P.M; m += gridDim.x * blockDim.x) {
-        int q = P.carry[m];
-        for (int j0 = 0; j0 < P.nb; j0 += 16) {
-            int l[16];
-#pragma unroll
-            for (int u = 0; u < 16; u++) l[u] = j0 + u < P.nb ? __ldg(P.last + (size_t)(j0 + u) * P.M + m) : -1;
-#pragma unroll
-            for (int u = 0; u < 16; u++)
-                if (j0 + u < P.nb) { P.Qtab[(size_t)(j0 + u) * P.M + m] = q; if (l[u] >= 0) q = l[u]; }
-        }
-        P.Qtab[(size_t)P.nb * P.M + m] = q;
-        P.carry[m] = q;
+    const size_t tot = (size_t)(P.nb + 1) * P.M;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i / P.M), m = (int)(i % P.M);
+        int q = -1;
+        int jj = j - 1;
+        for (; jj >= 0; jj--) { q = __ldg(P.last + (size_t)jj * P.M + m); if (q >= 0) break; }
+        if (jj < 0) q = P.carry[m];
+        P.Qtab[i] = q;
     }
 }
 
-// finality check of the listed rows of all blocks at once (see the header); thread per event picks the
-// listed ones, the warp then checks them one by one across the columns
+// finality check of the listed rows of all blocks at once (see the header): the items are every member's last event
+// of every block, and the rows a later block reads (xlist; one of those that is also a last event is taken once)
 __global__ void __launch_bounds__(256) k_cs_check(CsParams P) {
     const int lane = threadIdx.x & 31, M = P.M;
-    const int end = P.first + P.n;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int base = P.first + wid * 32; base < end; base += nw * 32) {
-        const int h = base + lane;
-        bool listed = false;
-        if (h < end) {
-            const int bh = cs_block_of(P, h);
-            listed = P.xb[h] || P.last[(size_t)bh * M + P.creator[h]] == h;
+    const int nlast = P.nb * M, total = nlast + P.slow_cnt[2];
+    for (int i = wid; i < total; i += nw) {
+        int x;
+        if (i < nlast) x = P.last[i];
+        else {
+            x = P.xlist[i - nlast];
+            if (P.last[(size_t)cs_block_of(P, x) * M + P.creator[x]] == x) x = -1;
         }
-        unsigned todo = __ballot_sync(0xffffffffu, listed);
-        while (todo) {
-            const int x = base + __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int bx = cs_block_of(P, x), lim = cs_start(P, bx);
-            const int32_t *Q = P.Qtab + (size_t)bx * M;
-            bool ok = true;
-            for (int c = lane; c < M; c += 32) {
-                const int pr = P.row[(size_t)x * M + c];
-                ok &= pr >= lim || pr == Q[c];
-            }
-            if (!__all_sync(0xffffffffu, ok) && lane == 0) {
-                P.slow_list[atomicAdd(&P.slow_cnt[0], 1)] = x;
-                atomicAdd(&P.slow_cnt[1], 1);
-                P.sflag[x] = 1;
-            }
+        if (x < 0) continue;
+        const int bx = cs_block_of(P, x), lim = cs_start(P, bx);
+        const int32_t *Q = P.Qtab + (size_t)bx * M;
+        bool ok = true;
+        for (int c = lane; c < M; c += 32) {
+            const int pr = P.row[(size_t)x * M + c];
+            ok &= pr >= lim || pr == Q[c];
+        }
+        if (!__all_sync(0xffffffffu, ok) && lane == 0) {
+            P.slow_list[atomicAdd(&P.slow_cnt[0], 1)] = x;
+            P.sflag[x] = 1;
         }
     }
 }
@@ -269,15 +278,24 @@ __global__ void __launch_bounds__(CS_SLOW_WARPS * 32) k_cs_slow(CsParams P) {
             }
             __syncwarp();
             if (!__all_sync(0xffffffffu, ready)) continue;
-            for (int c = lane; c < M; c += 32) {
-                const int pr = P.row[(size_t)x * M + c];
-                if (pr >= lim) continue;
-                int acc = pr;
-                for (int m = 0; m < M; m++) {
-                    const int ev = ent[m];
-                    if (ev >= 0) acc = max(acc, __ldcg(P.row + (size_t)ev * M + c));
+            // only the columns that are neither in-block nor the head itself can still grow: max over the entry events
+            for (int c0 = 0; c0 < M; c0 += 32) {
+                const int c = c0 + lane;
+                bool bad = false;
+                if (c < M) { const int pr = P.row[(size_t)x * M + c]; bad = pr < lim && pr != Q[c]; }
+                unsigned todo = __ballot_sync(0xffffffffu, bad);
+                while (todo) {
+                    const int cb = c0 + __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    int acc = -1;
+                    for (int m = lane; m < M; m += 32) {
+                        const int ev = ent[m];
+                        if (ev >= 0) acc = max(acc, __ldcg(P.row + (size_t)ev * M + cb));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+                    if (lane == 0 && acc > P.row[(size_t)x * M + cb]) P.row[(size_t)x * M + cb] = acc;
                 }
-                if (acc != pr) P.row[(size_t)x * M + c] = acc;
             }
             __syncwarp();
             if (lane == 0) { P.sflag[x] = 3; atomicSub(&left_s, 1); }

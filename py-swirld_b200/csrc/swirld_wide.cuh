@@ -95,15 +95,24 @@ __device__ __forceinline__ unsigned vcount_gt(const int *ev, int M, const unsign
         VCounter vc;
         vc.clear();
         const int iters = (M + G - 1) / G;
-        for (int it0 = 0; it0 < iters; it0 += 16) {
-            unsigned x[16];
+        auto fetch = [&](int it0, unsigned (&x)[16]) {
 #pragma unroll
             for (int u = 0; u < 16; u++) {
                 const int m = (it0 + u) * G + g;
                 const int k = (it0 + u < iters && m < M) ? ev[m] : -1;
                 x[u] = k >= 0 ? __ldcg(masks + (size_t)k * NJ + w) : 0u;
             }
-            vc.add16(x);
+        };
+        // two batches of 16 mask words in flight: the next one is fetched before the current one is added
+        unsigned xa[16], xb[16];
+        fetch(0, xa);
+        for (int it0 = 0; it0 < iters; it0 += 32) {
+            if (it0 + 16 < iters) fetch(it0 + 16, xb);
+            vc.add16(xa);
+            if (it0 + 16 < iters) {
+                if (it0 + 32 < iters) fetch(it0 + 32, xa);
+                vc.add16(xb);
+            }
         }
 #pragma unroll
         for (int d = NJ; d < 32; d <<= 1) vc.add_lane_xor(d);
@@ -153,6 +162,7 @@ struct RwParams {
     int32_t *ccnt, *cmin, *coff, *ctot, *gchain;
     unsigned *bar;
     u64 *hitmin;                // [3][M]
+    unsigned *ticket;           // [3] work counter of a step's tests (cleared like hitmin)
     const i64 *stake;
     i64 tot2;
     int unit;
@@ -221,9 +231,9 @@ __device__ __forceinline__ u64 rw_tag(int r, unsigned epoch) { return ((u64)epoc
 
 // publish S_r(k) (lane w < NJ holds word w) with its tag; readers: tag first (acquire), then the words
 template <int NJ>
-__device__ __forceinline__ void rw_publish(const RwParams &P, int k, unsigned word, u64 tag, int lane) {
+__device__ __forceinline__ void rw_publish(const RwParams &P, int k, unsigned word, u64 tag, int lane, bool fence = true) {
     if (lane < NJ) P.scw[(size_t)k * NJ + lane] = word;
-    __threadfence();
+    if (fence) __threadfence();          // (not needed when a grid barrier separates the producers from the readers)
     __syncwarp();
     if (lane == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(P.sctag + k), "l"(tag) : "memory");
 }
@@ -282,6 +292,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
         }
     }
     if (lead) for (int i = tid; i < 3 * M; i += RW_THREADS) P.hitmin[i] = ~0ull;
+    if (lead && tid < 3) P.ticket[tid] = 0;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0}, c_tests = 0, c_full = 0, c_tmax = 0;
     unsigned bar_target = 0;
     rw_grid_barrier(P.bar, bar_target);                 // roots are in the global table, hitmin is clear
 
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
     bool abort_all = false;
     unsigned step = 0;
     for (;; ++step) {
+        const long long t0 = clock64();
         // ---- lowest open round
         int rmin = 0x7fffffff;
         for (int c = tid; c < M; c += RW_THREADS) if (pos[c] < len[c]) rmin = min(rmin, cur[c]);
@@ -368,6 +381,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
             if (lane == 31) rbase[M] = inc;
         }
         __syncthreads();
+        const long long t1 = clock64();
         {   // ---- (a) masks of the new events below the frontier
             const int total = rbase[M];
             for (int i = gw; i < total; i += nw) {
@@ -380,16 +394,25 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
                 if (k < 0) continue;
                 if (rw_ld_tag(P.sctag + k) == tag) continue;          // prepared by an earlier launch step of this round
                 const unsigned word = seen_words<NJ>(P.row + (size_t)k * M, Wc, M, lane);
-                rw_publish<NJ>(P, k, word, tag, lane);
+                rw_publish<NJ>(P, k, word, tag, lane, false);
             }
         }
+        const long long t2 = clock64();
         rw_grid_barrier(P.bar, bar_target);
+        const long long t3 = clock64();
         // ---- (b) tests: one warp per (chain, tested position); with several ranks, my share of the chains
         {
+            // work items: (my chain, tested position) pairs, handed out by a ticket counter (a test that ends at the
+            // cheap live-stake check frees its warp for the next one)
             const int nown = (M - P.rank + P.nranks - 1) / P.nranks;
-            for (int i = gw; i < nown * RW_LMAX; i += nw) {
+            for (;;) {
+                unsigned tk = 0;
+                if (lane == 0) tk = atomicAdd(P.ticket + buf, 1u);
+                const int i = (int)__shfl_sync(0xffffffffu, tk, 0);
+                if (i >= nown * RW_LMAX) break;
                 const int tc = (i / RW_LMAX) * P.nranks + P.rank, tj = i % RW_LMAX;
                 if (tj >= ntest[tc]) continue;
+                const long long tt0 = clock64();
                 const int th = P.cev[off[tc] + pos[tc] + tj];
                 const int tpa = P.p0[th];
                 if (tpa < 0) continue;                                  // a root is never promoted
@@ -414,6 +437,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
                     }
                 }
                 __syncwarp();
+                c_tests++;
                 if (lv <= thr) continue;                                // hits[c_] <= stake of the live members
                 // a mask outside the prepared ranges (an event older than the ring): checked by tag, computed here
                 for (int c0 = 0; c0 < M; c0 += 32) {
@@ -436,9 +460,13 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
                 if ((i64)cnt > thr && lane == 0) atomicMin(P.hitmin + (size_t)buf * M + tc, ((u64)tj << 32) | (unsigned)th);
+                const long long dt = clock64() - tt0;
+                c_full++; c_tmax = dt > c_tmax ? dt : c_tmax;
             }
         }
+        const long long t4 = clock64();
         rw_grid_barrier(P.bar, bar_target);
+        const long long t5 = clock64();
         // ---- several GPUs: my chains' first hits go to every rank (P2P stores over NVLink), then one flag per peer
         const u64 *hsrc = P.hitmin + (size_t)buf * M;
         if (P.nranks > 1) {
@@ -490,12 +518,21 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
         if (lead) {                                     // clear the buffer the step after next will use
             const int nb2 = (buf + 2) % 3;
             for (int c = tid; c < M; c += RW_THREADS) P.hitmin[(size_t)nb2 * M + c] = ~0ull;
+            if (tid == 0) P.ticket[nb2] = 0;
         }
         for (int i = blockIdx.x + gridDim.x * tid; i < M * RW_LMAX; i += gridDim.x * RW_THREADS) {
             const int c = i / RW_LMAX, j = i % RW_LMAX;
             if (j < s_nfin[c]) P.round[P.cev[s_base[c] + j]] = rmin;
         }
         __syncthreads();
+        const long long t6 = clock64();
+        cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3; cyc[4] += t5 - t4; cyc[5] += t6 - t5;
+    }
+    if (P.dbg && lane == 0) {            // profiling counters (tools/rounds_cycles.py): [0..5] setup, masks, barrier, tests, barrier(+exchange), bookkeeping
+        unsigned long long *o = (unsigned long long *)P.dbg;
+        if (lead && warp == 0) { for (int i = 0; i < 6; i++) atomicAdd(&o[i], (unsigned long long)cyc[i]); atomicAdd(&o[6], (unsigned long long)step); }
+        atomicAdd(&o[9], (unsigned long long)c_tests); atomicAdd(&o[10], (unsigned long long)c_full);
+        atomicMax(&o[8], (unsigned long long)c_tmax);
     }
     if (lead && tid == 0 && P.n > 0) P.scal[SC_MAX_ROUND] = rtop;
     if (lead && tid == 0 && P.nranks > 1) *P.xstep = xbase + step;

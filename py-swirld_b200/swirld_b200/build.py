@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libswirld_b200.so")
 SOURCES = ["swirld_b200.cu"]
-DEPS = ["swirld_b200.cu", "swirld_kernels.cuh", "swirld_cansee.cuh", "swirld_rounds.cuh", "swirld_wide.cuh",
+DEPS = ["swirld_b200.cu", "swirld_kernels.cuh", "swirld_cansee.cuh", "swirld_rounds.cuh", "swirld_wide.cuh", "swirld_stream.cuh",
         "../../include/swirld_b200.h"]
 
 NVCC_FLAGS = [

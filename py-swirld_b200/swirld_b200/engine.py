@@ -24,6 +24,7 @@ SYMBOLS = [
     "sw_n_transactions", "sw_get_round", "sw_get_witness_flags", "sw_get_famous", "sw_get_can_see",
     "sw_get_witness_table", "sw_get_consensus", "sw_get_transactions", "sw_get_idx", "sw_get_height",
     "sw_sync", "sw_stats", "sw_flush_l2", "sw_version", "sw_debug_counters", "sw_peer_handle", "sw_peer_connect",
+    "sw_save", "sw_load", "sw_members", "sw_ingest", "sw_lookup",
 ]
 
 
@@ -81,6 +82,11 @@ def load_library(path: str = LIB_PATH):
     L.sw_debug_counters.argtypes = [vp, vp, i32]
     L.sw_peer_handle.argtypes = [vp, vp]
     L.sw_peer_connect.argtypes = [vp, i32, i32, vp]
+    L.sw_members.argtypes = [vp]
+    L.sw_ingest.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.sw_lookup.argtypes = [vp, i32, vp, vp]
+    L.sw_save.argtypes = [vp, C.c_char_p]
+    L.sw_load.argtypes = [C.c_char_p, i32, i32, P(vp)]
     _lib = L
     return L
 
@@ -104,6 +110,23 @@ class Engine:
         if rc < 0:
             raise EngineError(rc, (self._lib.sw_last_error(None) or b"").decode())
         self._h = h
+
+    # -- checkpoint / resume
+    def save(self, path: str):
+        self._chk(self._lib.sw_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, capacity: int = 0) -> "Engine":
+        lib = load_library()
+        h = C.c_void_p()
+        rc = lib.sw_load(os.fsencode(path), device, capacity, C.byref(h))
+        if rc < 0:
+            raise EngineError(rc, (lib.sw_last_error(None) or b"").decode())
+        self = cls.__new__(cls)
+        self._lib, self._h = lib, h
+        self.M = self._chk(lib.sw_members(h))
+        self.capacity = capacity
+        return self
 
     # -- life cycle
     def close(self):
@@ -149,6 +172,25 @@ class Engine:
         n = p0.shape[0]
         assert p1.shape[0] == n and creator.shape[0] == n and t.shape[0] == n and sig.size == 64 * n
         self._chk(self._lib.sw_append(self._h, n, _ptr(p0), _ptr(p1), _ptr(creator), _ptr(t), _ptr(sig)))
+
+    def ingest(self, ids, p0_ids, p1_ids, creator, t, sig):
+        """sw_ingest: events named by 32-byte ids (parents by id, zeros = none), any order; returns the arrival index
+        of every input event (-1 = rejected) and the number appended."""
+        ids = np.ascontiguousarray(ids, np.uint8).reshape(-1, 32)
+        n = ids.shape[0]
+        p0_ids = np.ascontiguousarray(p0_ids, np.uint8).reshape(n, 32)
+        p1_ids = np.ascontiguousarray(p1_ids, np.uint8).reshape(n, 32)
+        creator = np.ascontiguousarray(creator, np.int32); t = np.ascontiguousarray(t, np.float64)
+        sig = np.ascontiguousarray(sig, np.uint8).reshape(n, 64)
+        out = np.empty(n, np.int32)
+        m = self._chk(self._lib.sw_ingest(self._h, n, _ptr(ids), _ptr(p0_ids), _ptr(p1_ids), _ptr(creator), _ptr(t), _ptr(sig), _ptr(out)))
+        return out, m
+
+    def lookup(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint8).reshape(-1, 32)
+        out = np.empty(ids.shape[0], np.int32)
+        self._chk(self._lib.sw_lookup(self._h, ids.shape[0], _ptr(ids), _ptr(out)))
+        return out
 
     def append_trace(self, tr, first=0, n=None):
         n = tr.N - first if n is None else n
@@ -243,6 +285,19 @@ class Engine:
         out = np.zeros(16, np.int64)
         self._chk(self._lib.sw_debug_counters(self._h, _ptr(out), 1 if clear else 0))
         return out
+
+    # -- several GPUs of one box, M > 64 (include/swirld_b200.h: sw_peer_handle / sw_peer_connect)
+    def peer_handle(self) -> bytes:
+        """The 64-byte CUDA IPC handle of this engine's exchange buffer."""
+        buf = C.create_string_buffer(64)
+        self._chk(self._lib.sw_peer_handle(self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def peer_connect(self, rank: int, nranks: int, handles: bytes):
+        """handles = the nranks handles concatenated in rank order; call before the first divide_rounds."""
+        assert len(handles) == 64 * nranks
+        buf = C.create_string_buffer(handles, len(handles))
+        self._chk(self._lib.sw_peer_connect(self._h, rank, nranks, C.cast(buf, C.c_void_p)))
 
     def flush_l2(self, nbytes=256 << 20):
         self._chk(self._lib.sw_flush_l2(self._h, nbytes))

@@ -1,17 +1,22 @@
-"""Helpers shared by the GpuNode tests: run the gossip simulation, then replay each
-node's own arrival trace + call schedule through a checker."""
-import contextlib
-import io
-
+"""Helpers shared by the bound-node tests: run a gossip simulation, then replay each node's own arrival trace +
+call schedule through a checker."""
 import numpy as np
 
+import host_sim
 from swirld_b200 import node as gnode
 from swirld_b200.traces import Trace
 
 
-def run_sim(n_nodes, n_turns, **kw):
-    with contextlib.redirect_stdout(io.StringIO()):
-        return gnode.test(n_nodes, n_turns, **kw)
+def bound_class(host_cls, engine_cls=None):
+    """bind(host_cls); the CPU tests inject the oracle as the engine by subclassing (the product never does)."""
+    cls = gnode.bind(host_cls)
+    if engine_cls is None:
+        return cls
+    return type("GpuNodeOverOracle", (cls,), {"_engine_cls": engine_cls})
+
+
+def run_sim(n_nodes, n_turns, engine_cls=None, host_cls=host_sim.HostNode, **kw):
+    return host_sim.run_sim(n_nodes, n_turns, bound_class(host_cls, engine_cls), **kw)
 
 
 def node_trace(nd):

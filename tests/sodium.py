@@ -1,9 +1,7 @@
-"""The seven libsodium calls the gossip layer needs (signing, BLAKE2b ids, CSPRNG).
-
-Crypto is outside the accelerated path: the
-consensus kernels only ever consume signature *bytes*.  `pysodium` is used when it is
-installed (the reference's dependency); otherwise the same primitives come from
-PyNaCl's bundled libsodium.
+"""The libsodium calls the tests' own gossip host (tests/host_sim.py) needs (signing, BLAKE2b ids, CSPRNG).
+Test infrastructure: crypto is outside the accelerated path -- the consensus
+kernels only ever consume signature *bytes*.  `pysodium` is used when it is installed (the reference's
+dependency); otherwise the same primitives come from PyNaCl's bundled libsodium.
 """
 from __future__ import annotations
 

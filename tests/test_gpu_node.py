@@ -1,4 +1,4 @@
-"""GpuNode over the real engine (GPU): the gossip simulation with real signatures;
+"""The bound node over the real engine (GPU): a gossip simulation with real signatures (tests/host_sim.py);
 each node's device state equals the oracle's replay of that node's own trace and call
 schedule (K = one sync per call: the streaming cadence of Node.main)."""
 import os
@@ -23,7 +23,7 @@ def _dump(tag, tr, sizes):
 
 @pytest.mark.parametrize("n_nodes,turns,cap", [(5, 400, 128), (4, 300, 1 << 12), (7, 350, 1 << 12)])
 def test_simulation_over_the_gpu_engine(n_nodes, turns, cap):
-    sim = node_sim.run_sim(n_nodes, turns, capacity=cap)      # small capacity: forces a growth replay
+    sim = node_sim.run_sim(n_nodes, turns, capacity=cap, seed=turns)      # small capacity: forces a growth replay
     for i, nd in enumerate(sim):
         tr, sizes = node_sim.node_trace(nd)
         try:
@@ -40,3 +40,25 @@ def test_simulation_over_the_gpu_engine(n_nodes, turns, cap):
     for nd in sim:
         assert len(set(nd.transactions)) == len(nd.transactions)
         assert [nd.idx[x] for x in nd.transactions] == list(range(len(nd.transactions)))
+
+
+def test_reference_node_bound_to_the_gpu_engine():
+    """Where the reference's files are available (baseline/_ref travels to the GPU box): `swirld.test` over
+    bind(swirld.Node) on the real engine, each node against the oracle's replay of its own trace and schedule."""
+    import contextlib
+    import io
+    import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("reference files not staged")
+    from swirld_b200 import node as gnode
+    swirld = rh.load_reference()
+    saved = swirld.Node
+    try:
+        swirld.Node = gnode.bind(saved)
+        with contextlib.redirect_stdout(io.StringIO()):
+            nodes = swirld.test(4, 250)
+    finally:
+        swirld.Node = saved
+    for nd in nodes:
+        tr, sizes = node_sim.node_trace(nd)
+        assert_same(node_sim.replay_oracle(tr, sizes), node_sim.node_results(nd), KEYS, "bind(swirld.Node) vs oracle replay")

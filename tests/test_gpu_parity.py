@@ -320,3 +320,99 @@ def test_headline_config3_full_length():
     assert_same(o, r, what="config 3 full length")
     assert np.array_equal(witness_flags_from_table(o["witness_table"], tr.N), r["witness"])
     _properties(tr, r)
+
+
+# ---------------------------------------------------------------- checkpoint / resume, native ingest
+@pytest.mark.parametrize("M,N,K", [(16, 20000, 700), (96, 20000, 3000)])
+def test_checkpoint_resume(M, N, K, tmp_path):
+    """Half the trace, sw_save, sw_load into a new (larger) engine, the other half on both: the resumed engine, the
+    uninterrupted one and the oracle agree on everything, the final order included."""
+    from swirld_b200 import engine, traces
+    from swirld_b200.traces import chunks
+    tr = traces.gossip(M, N, 81)
+    o = orc.run_oracle(tr, K)
+    sched = list(chunks(N, K))
+    half = len(sched) // 2
+    e = engine.Engine(M, N)
+    ncs = []
+    for first, cnt in sched[:half]:
+        e.append_trace(tr, first, cnt)
+        e.divide_rounds(first, cnt)
+        nc = e.decide_fame()
+        e.find_order(nc)
+        ncs.append(sorted(nc))
+    path = str(tmp_path / "ckpt.swb")
+    e.save(path)
+    e2 = engine.Engine.load(path, capacity=N + 1000)
+    assert e2.M == M and e2.n_events == e.n_events and e2.n_divided == e.n_divided and e2.n_transactions == e.n_transactions
+    assert np.array_equal(e.can_see(), e2.can_see())
+    outs = []
+    for eng in (e, e2):
+        calls = list(ncs)
+        for first, cnt in sched[half:]:
+            eng.append_trace(tr, first, cnt)
+            eng.divide_rounds(first, cnt)
+            nc = eng.decide_fame()
+            eng.find_order(nc)
+            calls.append(sorted(nc))
+        r = eng.results()
+        r["new_c_per_call"] = calls
+        outs.append(r)
+    assert_same(o, outs[0], what="uninterrupted")
+    assert_same(o, outs[1], what="resumed from the checkpoint")
+    assert np.array_equal(o["oracle"].can_see(), e2.can_see())
+
+
+def test_native_ingest_orders_and_validates():
+    """sw_ingest: events by 32-byte id in a shuffled batch -> parents-first order, known ids skipped, forks and orphans
+    (and what hangs below them) rejected; consensus on the ingested graph equals the oracle on the same arrival order."""
+    import hashlib
+    from swirld_b200 import engine, traces
+    tr = traces.gossip(12, 6000, 91)
+    N = tr.N
+    ids = np.stack([np.frombuffer(hashlib.blake2b(b"ev%d" % i, digest_size=32).digest(), np.uint8) for i in range(N)])
+    zero = np.zeros(32, np.uint8)
+    pid = lambda a: np.stack([ids[x] if x >= 0 else zero for x in a])
+    e = engine.Engine(12, N + 8)
+    rng = np.random.default_rng(5)
+    arrival = np.full(N, -1, np.int64)
+    first = 0
+    for cnt in [12, 1, 7, 500, 3, 2477, 3000]:
+        sl = np.arange(first, first + cnt)
+        perm = rng.permutation(sl)                        # the batch arrives in any order
+        extra = perm[:min(3, first)] - first if first else perm[:0]
+        batch = np.concatenate([perm, rng.integers(0, first, 2) if first else perm[:0]]).astype(np.int64)   # + two known events
+        out, m = e.ingest(ids[batch], pid(tr.p0[batch]), pid(tr.p1[batch]), tr.creator[batch], tr.t[batch], tr.sig[batch])
+        assert m == cnt and np.all(out >= 0)
+        assert np.array_equal(np.sort(out[:cnt]), np.arange(first, first + cnt))      # the new ones got the next indices
+        arrival[batch[:cnt]] = out[:cnt]
+        assert np.array_equal(out[cnt:], arrival[batch[cnt:]])                        # known ids: their old index
+        first += cnt
+    assert np.array_equal(e.lookup(ids[:50]), arrival[:50])
+    # rejected: a fork (second child on an old self-parent), an orphan (unknown parent), and the orphan's child
+    bad_ids = np.stack([np.frombuffer(hashlib.blake2b(b"bad%d" % i, digest_size=32).digest(), np.uint8) for i in range(3)])
+    c0 = int(tr.creator[100])
+    other = int(np.nonzero(tr.creator[:100] != c0)[0][-1])
+    p0s = np.stack([ids[100], bad_ids[2] ^ 0xFF, bad_ids[1]])
+    p1s = np.stack([ids[other], ids[other], ids[other]])
+    crs = np.array([c0, c0, c0], np.int32)
+    out, m = e.ingest(bad_ids, p0s, p1s, crs, np.zeros(3), np.zeros((3, 64), np.uint8))
+    assert m == 0 and out.tolist() == [-1, -1, -1] and e.n_events == N
+    # consensus on the ingested graph == the oracle on the same arrival order
+    order = np.argsort(arrival)
+    inv = arrival
+    from swirld_b200.traces import Trace
+    remap = lambda p: np.where(p >= 0, inv[np.maximum(p, 0)], -1).astype(np.int32)
+    tr2 = Trace(12, remap(tr.p0[order]), remap(tr.p1[order]), tr.creator[order], tr.t[order], tr.sig[order], "ingested")
+    K = 900
+    o = orc.run_oracle(tr2, K)
+    from swirld_b200.traces import chunks
+    ncs = []
+    for f0, cnt in chunks(N, K):
+        e.divide_rounds(f0, cnt)
+        nc = e.decide_fame()
+        e.find_order(nc)
+        ncs.append(sorted(nc))
+    r = e.results()
+    r["new_c_per_call"] = ncs
+    assert_same(o, r, what="ingested graph")

@@ -1,8 +1,8 @@
-"""GpuNode's host logic on CPU: the reference's gossip simulation (real Ed25519
-signatures, BLAKE2b ids, random peers) runs over GpuNode with the oracle standing in
-for the device; every node's state must equal a replay of its own arrival trace and
-call schedule through the oracle and -- where /root/reference is mounted -- through
-the unmodified reference."""
+"""The bound node's host logic on CPU: a gossip simulation (real Ed25519 signatures, BLAKE2b ids, random peers)
+runs over `bind(host)` with the oracle standing in for the device -- over the tests' own host everywhere, and over
+the reference's `swirld.Node` itself (its `sync` / `ask_sync` / `new_event` / `main` inherited unchanged) where the
+reference is available; every node's state must equal a replay of its own arrival trace and call schedule through
+the oracle and through the unmodified reference."""
 import pytest
 
 import node_sim
@@ -13,13 +13,9 @@ from util import assert_same
 KEYS = ["round", "famous", "consensus", "transactions"]
 
 
-def _factory(M, cap, stake, C):
-    return OracleEngine(M, cap, stake, C)
-
-
 @pytest.fixture(scope="module")
 def sim():
-    return node_sim.run_sim(4, 400, engine_factory=_factory, capacity=64)   # small capacity: forces growth replay
+    return node_sim.run_sim(4, 400, OracleEngine, capacity=64, seed=5)   # small capacity: forces growth replay
 
 
 def test_transactions_are_consistent(sim):
@@ -62,20 +58,17 @@ def test_each_node_matches_reference_replay(sim):
         assert_same(node_sim.replay_reference(tr, sizes), node_sim.node_results(nd), KEYS, "node vs reference replay")
 
 
-@pytest.mark.skipif(not rh.reference_available(), reason="reference not mounted (GPU box)")
+@pytest.mark.skipif(not rh.reference_available(), reason="reference not available")
 def test_drop_in_for_the_reference_drivers():
-    """`swirld.Node = GpuNode` before `swirld.test(...)`: the reference's own driver and
-    main loop run unchanged over the replacement class."""
+    """`swirld.Node = bind(swirld.Node)` before `swirld.test(...)`: the reference's own driver, main loop, sync and
+    event code run unchanged (inherited) over the GPU-backed consensus state."""
     import contextlib
-    import functools
     import io
     swirld = rh.load_reference()
-    from swirld_b200 import node as gnode
     saved = swirld.Node
     try:
-        swirld.Node = functools.partial(gnode.GpuNode, engine_factory=_factory)
-        import random
-        random.seed(20260922)           # the driver gossips with the global RNG (the key pairs stay random)
+        swirld.Node = node_sim.bound_class(saved, OracleEngine)
+        assert swirld.Node.sync is saved.sync and swirld.Node.main is saved.main and swirld.Node.new_event is saved.new_event
         with contextlib.redirect_stdout(io.StringIO()):
             nodes = swirld.test(4, 300)
     finally:
@@ -84,3 +77,38 @@ def test_drop_in_for_the_reference_drivers():
     for nd in nodes:       # each node equals the reference's replay of its own trace + schedule
         tr, sizes = node_sim.node_trace(nd)
         assert_same(node_sim.replay_reference(tr, sizes), node_sim.node_results(nd), KEYS, "drop-in node vs reference")
+
+
+def test_forked_events_are_dropped_not_fatal():
+    """A Byzantine peer's fork (a second event on the same self-parent) is treated as invalid: the node keeps working
+    and its device state stays consistent (the reference would accept the fork; the engine's contract is fork-free)."""
+    import host_sim
+    nodes = node_sim.run_sim(3, 60, OracleEngine, seed=9)
+    a, b = nodes[0], nodes[1]
+    # b forges a sibling of its own head: same self-parent, other other-parent
+    sp = b.hg[b.head].p
+    assert sp
+    other = next(h for h in b.hg if b.hg[h].c != b.pk and h != sp[1])
+    h2, ev2 = host_sim.HostNode.new_event(b, "fork", (sp[0], other))
+    assert host_sim.HostNode.is_valid_event(a, h2, ev2) or other not in a.hg or sp[0] not in a.hg
+    n_before = len(a.hg)
+    if sp[0] in a.hg and other in a.hg and a._heads.get(b.pk) != sp[0]:
+        assert not a.is_valid_event(h2, ev2)             # a already holds b's real event on that self-parent
+    # a second root is always a fork
+    hr, evr = host_sim.HostNode.new_event(b, None, ())
+    assert not a.is_valid_event(hr, evr)
+    assert len(a.hg) == n_before
+    loop = a.main()
+    next(loop)
+    loop.send(None)                                      # the node still gossips and advances
+    assert len(a.hg) > n_before
+    tr, sizes = node_sim.node_trace(a)
+    assert_same(node_sim.replay_oracle(tr, sizes), node_sim.node_results(a), KEYS, "after the rejected fork")
+
+
+def test_non_integral_stake_is_refused():
+    import host_sim
+    import sodium
+    kp = sodium.crypto_sign_keypair()
+    with pytest.raises(ValueError):
+        node_sim.bound_class(host_sim.HostNode, OracleEngine)(kp, {}, 1, {kp[0]: 1.5})
