@@ -413,6 +413,41 @@ def bench_ours(args, wl, rank, world, local_rank):
     got_round, got_wit, got_fam = eng.rounds(), eng.witness_flags(), eng.famous()
     check = (int(got_round.astype(np.int64).sum()), int(eng.max_round), int(len(eng.consensus())))
 
+    # ---- several node-views per launch (M <= 64: SURVEY.md section 8f-3): B independent views (own traces) advanced by
+    #      sw_batch_divide_rounds, aggregate events/s over all views, device-timed on the first view's stream
+    views_out = None
+    if args.views and not shard and M <= 64:
+        views_out = []
+        Nv = min(N, args.views_events) if args.views_events else N
+        for B in [int(x) for x in args.views.split(",")]:
+            trs = [make_trace(dict(wl, N=Nv), 1000 + 17 * rank + v) for v in range(B)]
+            engs = [engine.Engine(M, Nv, device=local_rank) for _ in range(B)]
+            for ev, tv in zip(engs, trs):
+                ev.append_trace(tv)
+            vs = list(chunks(Nv, K))
+            best = None
+            for rep_i in range(1 + max(1, args.steps // 4)):
+                for ev in engs:
+                    ev.rewind()
+                torch.cuda.synchronize()
+                t0v = time.perf_counter()
+                for first, cnt in vs:
+                    engine.batch_divide_rounds(engs, [first] * B, [cnt] * B)
+                    for ev in engs:
+                        ev.decide_fame()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0v
+                if rep_i and (best is None or dt < best):      # (the first pass is the warm-up)
+                    best = dt
+            ok_v = True
+            if B <= 8:
+                ov = run_cpu_pass(trs[-1], K)[3]
+                ok_v = bool(np.array_equal(ov["round"], engs[-1].rounds()) and np.array_equal(ov["famous"], engs[-1].famous()))
+            views_out.append({"views": B, "events_per_view": Nv, "events_per_s": B * Nv / best, "ms": best * 1e3,
+                              "last_view_equals_oracle": ok_v})
+            for ev in engs:
+                ev.close()
+
     # ---- find_order, timed separately (not part of the metric); every rank runs it (replicated)
     fo_ms, n_ordered = None, None
     if not args.no_find_order and M <= 256:
@@ -556,6 +591,7 @@ def bench_ours(args, wl, rank, world, local_rank):
                 "events_per_s": n_ordered / (fo_ms * 1e-3) if fo_ms > 0 else None, "ordered": int(n_ordered),
                 "ms": fo_ms, "cpu_port_events_per_s": n_cpu / fo_cpu if fo_cpu > 0 else None},
             "checksum": {"round_sum": check[0], "max_round": check[1], "consensus_rounds": check[2]},
+            "views": views_out,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -573,6 +609,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--events", type=int, default=0, help="override the workload's event count")
     ap.add_argument("--no-find-order", action="store_true")
+    ap.add_argument("--views", default="", help="comma list of view counts B for the multi-view leg (M <= 64), e.g. 1,8,32")
+    ap.add_argument("--views-events", type=int, default=0, help="events per view in the multi-view leg (default: the workload's)")
     ap.add_argument("--no-python-reference", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

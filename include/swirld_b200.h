@@ -87,6 +87,13 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1,
  * `first` must equal the number of events already divided. Asynchronous. */
 int sw_divide_rounds(sw_engine *e, int first, int n);
 
+/* Node.divide_rounds for B independent node-views in one call (the simulation's M nodes each recompute consensus on
+ * nearly the same graph, swirld.py:331-345 / viz.py:35-46): engines[v] divides its events [first[v], first[v]+n[v]).
+ * M <= 64, same member count and stake shape, same device.  The views' round kernels advance side by side in ONE
+ * cooperative launch (each on its own group of CTAs): the path is latency-bound, so this is what fills the GPU.
+ * Results per view are identical to B separate sw_divide_rounds calls. */
+int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, const int *n);
+
 /* Node.decide_fame() (swirld.py:224-277).  Writes the new consensus rounds
  * (ascending) to new_c_out[0..cap) and returns their count. */
 int sw_decide_fame(sw_engine *e, int32_t *new_c_out, int cap);

@@ -61,6 +61,9 @@ struct sw_engine {
     int32_t *d_Wf = nullptr, *d_cev = nullptr, *d_rbmeta = nullptr, *d_rbtot = nullptr, *d_gchain = nullptr;   // round-batch state
     ulonglong2 *d_sc = nullptr;
     uint8_t *d_res = nullptr;
+    RbParams *d_views = nullptr;  // sw_batch_divide_rounds: the views' parameters (owned by the first engine of a batch)
+    int views_cap = 0;
+    cudaEvent_t view_ev = nullptr;
     int n_rowed = 0;              // events whose can_see row is complete
     // can_see scan scratch (swirld_cansee.cuh)
     int4 *d_cs_meta = nullptr;
@@ -301,15 +304,11 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     return 0;
 }
 
-// rounds of the chunk by the cooperative round-batch kernel (swirld_rounds.cuh), M <= 64
-template <int NC, bool UNIT>
-int divide_round_batch(sw_engine *e, int first, int n) {
-    RbParams R{};
+// rounds of the chunk by the cooperative round-batch kernel (swirld_rounds.cuh), M <= 64: parameters + the kernels
+// that group the chunk's events by creator (`grid` = CTAs this view's round kernel will run on)
+int round_batch_prep(sw_engine *e, int first, int n, int grid, RbParams &R) {
+    R = RbParams{};
     R.M = e->M; R.first = first; R.n = n; R.Rcap = e->Rcap;
-    // a few SMs stay free for the can_see scan of the next chunk, which runs beside this kernel (SW_RB_FREE_SMS)
-    int free_sms = 16;
-    if (const char *v = getenv("SW_RB_FREE_SMS")) free_sms = std::max(0, atoi(v));
-    const int grid = std::max(e->n_sm / 2, e->n_sm - free_sms);
     R.L = std::max(1, std::min(RB_LMAX, grid * (RB_THREADS / 32) / e->M));
     R.maxmiss = RB_MAXMISS;
     R.epoch = ++e->rb_epoch;
@@ -329,21 +328,19 @@ int divide_round_batch(sw_engine *e, int first, int n) {
     k_rb_offsets<<<1, 32, 0, e->stream>>>(R);
     k_rb_scatter<<<blocks, 256, 0, e->stream>>>(R);
     CK(cudaGetLastError());
-    void *args[] = {(void *)&R};
-    {
-        cudaEvent_t a = get_event(e), b = get_event(e);
-        cudaEventRecord(a, e->stream);
-        CK(cudaLaunchCooperativeKernel((void *)k_rounds_batch<NC, UNIT>, dim3(grid), dim3(RB_THREADS), args, 0, e->stream));
-        cudaEventRecord(b, e->stream);
-        e->spans.push_back(TimedSpan{a, b, 4});
-    }
+    return 0;
+}
+
+// what follows the round kernel: ring of recent events, witness flags / table / list, seen-masks, strongly-seen sets
+template <int NC>
+int round_batch_finish(sw_engine *e, const RbParams &R) {
+    const int n = R.n, blocks = std::max(1, std::min(296, (n + 255) / 256));
     k_rb_tail<<<blocks, 256, 0, e->stream>>>(R);
     k_rb_witness<<<blocks, 256, 0, e->stream>>>(R);
     k_rb_seenmask<NC><<<(n + 7) / 8, 256, 0, e->stream>>>(R);
     CK(cudaGetLastError());
-    // decide_fame's strongly-seen sets of the chunk's witnesses
     StrongParams Q{};
-    Q.M = e->M; Q.first = first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
+    Q.M = e->M; Q.first = R.first; Q.n = n; Q.Rcap = e->Rcap; Q.creator = e->d_creator; Q.row = e->d_row;
     Q.round = e->d_round; Q.wit = e->d_wit; Q.SM = e->d_SM; Q.S = e->d_S; Q.stake = e->d_stake; Q.tot2 = 2 * e->tot;
     Q.coin = e->d_coin; Q.sig = e->d_sig; Q.unit = e->unit ? 1 : 0;
     Q.list = R.wlist; Q.list_n = R.wcnt;
@@ -352,6 +349,25 @@ int divide_round_batch(sw_engine *e, int first, int n) {
     CK(cudaGetLastError());
     e->stats.kernel_launches += 8;
     return 0;
+}
+
+template <int NC, bool UNIT>
+int divide_round_batch(sw_engine *e, int first, int n) {
+    // a few SMs stay free for the can_see scan of the next chunk, which runs beside this kernel (SW_RB_FREE_SMS)
+    int free_sms = 16;
+    if (const char *v = getenv("SW_RB_FREE_SMS")) free_sms = std::max(0, atoi(v));
+    const int grid = std::max(e->n_sm / 2, e->n_sm - free_sms);
+    RbParams R;
+    if (round_batch_prep(e, first, n, grid, R) < 0) return SW_E_CUDA;
+    void *args[] = {(void *)&R};
+    {
+        cudaEvent_t a = get_event(e), b = get_event(e);
+        cudaEventRecord(a, e->stream);
+        CK(cudaLaunchCooperativeKernel((void *)k_rounds_batch<NC, UNIT>, dim3(grid), dim3(RB_THREADS), args, 0, e->stream));
+        cudaEventRecord(b, e->stream);
+        e->spans.push_back(TimedSpan{a, b, 4});
+    }
+    return round_batch_finish<NC>(e, R);
 }
 
 size_t rounds_wide_smem(int M) { return (size_t)(2 * M + 16 * M + 1 + 32 + (RW_THREADS / 32) * M + 1) * sizeof(int); }
@@ -541,6 +557,8 @@ void sw_destroy(sw_engine *e) {
     for (auto ev : e->pool) cudaEventDestroy(ev);
     for (auto ev : e->user_ev) if (ev) cudaEventDestroy(ev);
     if (e->scan_ev) cudaEventDestroy(e->scan_ev);
+    if (e->view_ev) cudaEventDestroy(e->view_ev);
+    if (e->d_views) cudaFree(e->d_views);
     for (auto ev : e->stage_ev) if (ev) cudaEventDestroy(ev);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->d_stage) cudaFree(e->d_stage);
@@ -741,6 +759,71 @@ int sw_divide_rounds(sw_engine *e, int first, int n) {
     }
     e->stats.events_divided += n;
     e->n_divided += n;
+    return SW_OK;
+}
+
+// Node.divide_rounds for B independent node-views at once (M <= 64, same member count, same device): everything of a
+// view runs on the view's own stream, except the round kernels, which advance side by side in ONE cooperative launch.
+int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, const int *n) {
+    sw_engine *e = (engines && B > 0) ? engines[0] : nullptr;
+    if (!e || !first || !n) return fail(e, SW_E_ARG, "bad argument");
+    for (int v = 0; v < B; v++) {
+        sw_engine *x = engines[v];
+        if (!x || x->wide || x->M != e->M || x->device != e->device || x->unit != e->unit)
+            return fail(e, SW_E_UNSUPPORTED, "sw_batch_divide_rounds: the views must be M <= 64 engines of one shape on one device");
+        if (n[v] <= 0 || first[v] != x->n_divided || first[v] + n[v] > x->n_events)
+            return fail(e, SW_E_ARG, "sw_batch_divide_rounds: view %d: bad range [%d,%d)", v, first[v], first[v] + n[v]);
+    }
+    CK(cudaSetDevice(e->device));
+    const int M = e->M, gmin = (M + RB_THREADS / 32 - 1) / (RB_THREADS / 32);    // a view needs one warp per member chain
+    const int per_launch = std::max(1, e->n_sm / gmin);
+    if (B > e->views_cap) {
+        if (e->d_views) cudaFree(e->d_views);
+        e->d_views = nullptr;
+        CK(cudaMalloc((void **)&e->d_views, sizeof(RbParams) * B));
+        e->views_cap = B;
+    }
+    if (!e->view_ev) CK(cudaEventCreateWithFlags(&e->view_ev, cudaEventDisableTiming));
+    std::vector<RbParams> Rv(B);
+    for (int v0 = 0; v0 < B; v0 += per_launch) {
+        const int nv = std::min(per_launch, B - v0), G = std::max(gmin, e->n_sm / nv);
+        for (int v = v0; v < v0 + nv; v++) {
+            sw_engine *x = engines[v];
+            if (first[v] + n[v] > x->n_rowed) {
+                if (wait_appends(x, -1) < 0) return SW_E_CUDA;
+                if (cansee_scan(x, x->stream, x->n_events) < 0) return SW_E_CUDA;
+                CK(cudaEventRecord(x->scan_ev, x->stream));
+                x->scan_ev_set = true;
+            } else if (wait_appends(x, first[v] + n[v]) < 0) return SW_E_CUDA;
+            if (round_batch_prep(x, first[v], n[v], G, Rv[v]) < 0) { e->err = x->err; return SW_E_CUDA; }
+            cudaEvent_t ev = get_event(x);
+            CK(cudaEventRecord(ev, x->stream));
+            CK(cudaStreamWaitEvent(e->stream, ev, 0));
+            x->pool.push_back(ev);
+        }
+        CK(cudaMemcpyAsync(e->d_views + v0, Rv.data() + v0, sizeof(RbParams) * nv, cudaMemcpyHostToDevice, e->stream));
+        const RbParams *pv = e->d_views + v0;
+        int g = G;
+        void *args[] = {(void *)&pv, (void *)&g};
+        {
+            cudaEvent_t a = get_event(e), b = get_event(e);
+            cudaEventRecord(a, e->stream);
+            void *fn = e->NC == 1 ? (e->unit ? (void *)k_rounds_batch_views<1, true> : (void *)k_rounds_batch_views<1, false>)
+                                  : (e->unit ? (void *)k_rounds_batch_views<2, true> : (void *)k_rounds_batch_views<2, false>);
+            CK(cudaLaunchCooperativeKernel(fn, dim3(nv * G), dim3(RB_THREADS), args, 0, e->stream));
+            cudaEventRecord(b, e->stream);
+            e->spans.push_back(TimedSpan{a, b, 4});
+        }
+        CK(cudaEventRecord(e->view_ev, e->stream));
+        CK(cudaStreamSynchronize(e->stream));       // (Rv / the event are reused by the next group; the views' finish kernels follow)
+        for (int v = v0; v < v0 + nv; v++) {
+            sw_engine *x = engines[v];
+            int rc = x->NC == 1 ? round_batch_finish<1>(x, Rv[v]) : round_batch_finish<2>(x, Rv[v]);
+            if (rc < 0) return rc;
+            x->stats.events_divided += n[v];
+            x->n_divided += n[v];
+        }
+    }
     return SW_OK;
 }
 

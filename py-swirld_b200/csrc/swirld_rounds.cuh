@@ -119,9 +119,9 @@ __global__ void k_rb_tail(RbParams P) {
 // counts arrivals for ever; the caller keeps the running target.  The whole of warp 0 polls, so no
 // warp leaves the barrier split in two (cooperative_groups' grid.sync() lets thread 0 spin alone and
 // its warp then runs every later shuffle on the slow divergent path).
-__device__ __forceinline__ void rb_grid_barrier(unsigned *ctr, unsigned &target) {
+__device__ __forceinline__ void rb_grid_barrier(unsigned *ctr, unsigned &target, unsigned ngrid) {
     __syncthreads();
-    target += gridDim.x;
+    target += ngrid;
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) { __threadfence(); atomicAdd(ctr, 1u); }
         __syncwarp();
@@ -138,8 +138,10 @@ __device__ __forceinline__ u64 rb_key(int r, unsigned epoch) {
     return (u64)(r + 1) * 0x9E3779B97F4A7C15ull ^ (u64)(epoch + 1) * 0xC2B2AE3D27D4EB4Full;
 }
 
+// (bx, gx): this CTA's index and the CTA count of ITS hashgraph -- the whole grid, or one view's share of it when
+// several independent node-views advance in one launch (k_rounds_batch_views)
 template <int NC, bool UNIT>
-__global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
+__device__ __forceinline__ void rounds_batch_body(const RbParams &P, const int bx, const int gx) {
     __shared__ int cur[64], pos[64], len[64], off[64];
     __shared__ int Wl[RB_WR][64], Wls[RB_WR][64];             // Wf of the last RB_WR rounds and the chain seq of its entries
     __shared__ i64 stake_s[64];
@@ -147,9 +149,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
     __shared__ int cmin_s[64], ctot_s[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M, L = P.L;
-    const int gw = blockIdx.x * (blockDim.x >> 5) + warp, nw = gridDim.x * (blockDim.x >> 5);
+    const int gw = bx * (blockDim.x >> 5) + warp, nw = gx * (blockDim.x >> 5);
     const i64 thr = P.tot2 / 3;
-    const bool lead = blockIdx.x == 0;
+    const bool lead = bx == 0;
     // per-step results, double buffered: first hit of a chain as (position << 32 | event), first deferred position
     // (three buffers: the tests of step s+1 start without a grid barrier after the bookkeeping of step s)
     u64 *hitmin = reinterpret_cast<u64 *>(P.res);             // [3][64]
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         }
     }
     unsigned bar_target = 0;
-    rb_grid_barrier(P.bar, bar_target);                       // (late roots write the global table only)
+    rb_grid_barrier(P.bar, bar_target, gx);                       // (late roots write the global table only)
 
     auto in_mirror = [&](int r) -> bool { return r > rtop - RB_WR && r <= rtop; };
     auto wrow = [&](int r, int c) -> int {                    // Wf_r[c]
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
             }
         }
         const long long t1 = clock64();
-        rb_grid_barrier(P.bar, bar_target);
+        rb_grid_barrier(P.bar, bar_target, gx);
         const long long t2 = clock64();
         // ---- identical bookkeeping in every CTA (only CTA 0 writes the global tables)
         int ft = -1, win = 0, hnew = -1;
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         }
         __syncthreads();
         // final rounds of the events before the first hit, spread over the CTAs
-        for (int i = blockIdx.x + gridDim.x * tid; i < M * RB_LMAX; i += gridDim.x * blockDim.x) {
+        for (int i = bx + gx * tid; i < M * RB_LMAX; i += gx * blockDim.x) {
             const int c = i / RB_LMAX, j = i % RB_LMAX;
             if (j < s_nfin[c]) P.round[P.cev[s_base[c] + j]] = rmin;
         }
@@ -501,12 +503,29 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
         atomicAdd((unsigned long long *)P.dbg + 13, (unsigned long long)c_g);
         atomicMax((unsigned long long *)P.dbg + 14, (unsigned long long)c_gmax);
     }
-    if (P.dbg && lane == 0 && warp == 0 && blockIdx.x == 0) {
+    if (P.dbg && lane == 0 && warp == 0 && bx == 0) {
         unsigned long long *o = (unsigned long long *)P.dbg;
         for (int i = 0; i < 6; i++) atomicAdd(&o[i], (unsigned long long)c_t[i]);
         atomicAdd(&o[6], (unsigned long long)c_steps);
     }
     if (lead && tid == 0 && P.n > 0) P.scal[SC_MAX_ROUND] = rtop;
+}
+
+template <int NC, bool UNIT>
+__global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch(RbParams P) {
+    rounds_batch_body<NC, UNIT>(P, blockIdx.x, gridDim.x);
+}
+
+// Several independent node-views (the simulation's M nodes each recompute consensus on nearly
+// the same graph, swirld.py:331-345) in ONE cooperative launch: view v runs on CTAs [v*G, (v+1)*G) with its own
+// parameters, barrier counter and result buffers.  The path is latency-bound (one grid-wide step per round), so G small
+// CTA groups advancing side by side use the GPU far better than one view on all of it.
+template <int NC, bool UNIT>
+__global__ void __launch_bounds__(RB_THREADS, 1) k_rounds_batch_views(const RbParams *Pv, int G) {
+    __shared__ RbParams Ps;
+    if (threadIdx.x == 0) Ps = Pv[blockIdx.x / G];
+    __syncthreads();
+    rounds_batch_body<NC, UNIT>(Ps, blockIdx.x % G, G);
 }
 
 // ---- the reference's witness flags / witnesses table from the finished rounds (swirld.py:221-222, 196-197)

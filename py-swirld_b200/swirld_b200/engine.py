@@ -24,7 +24,7 @@ SYMBOLS = [
     "sw_n_transactions", "sw_get_round", "sw_get_witness_flags", "sw_get_famous", "sw_get_can_see",
     "sw_get_witness_table", "sw_get_consensus", "sw_get_transactions", "sw_get_idx", "sw_get_height",
     "sw_sync", "sw_stats", "sw_flush_l2", "sw_version", "sw_debug_counters", "sw_peer_handle", "sw_peer_connect",
-    "sw_save", "sw_load", "sw_members", "sw_ingest", "sw_lookup",
+    "sw_save", "sw_load", "sw_members", "sw_ingest", "sw_lookup", "sw_batch_divide_rounds",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library(path: str = LIB_PATH):
     L.sw_members.argtypes = [vp]
     L.sw_ingest.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.sw_lookup.argtypes = [vp, i32, vp, vp]
+    L.sw_batch_divide_rounds.argtypes = [vp, i32, vp, vp]
     L.sw_save.argtypes = [vp, C.c_char_p]
     L.sw_load.argtypes = [C.c_char_p, i32, i32, P(vp)]
     _lib = L
@@ -307,6 +308,15 @@ class Engine:
         return {"round": self.rounds(), "witness": self.witness_flags(),
                 "witness_table": self.witness_table(), "famous": self.famous(),
                 "consensus": self.consensus(), "transactions": self.transactions()}
+
+
+def batch_divide_rounds(engines, firsts, counts):
+    """sw_batch_divide_rounds: divide_rounds of several independent node-views (M <= 64) in one call."""
+    B = len(engines)
+    arr = (C.c_void_p * B)(*[e._h for e in engines])
+    f = np.ascontiguousarray(firsts, np.int32)
+    n = np.ascontiguousarray(counts, np.int32)
+    engines[0]._chk(engines[0]._lib.sw_batch_divide_rounds(C.cast(arr, C.c_void_p), B, _ptr(f), _ptr(n)))
 
 
 def run_engine(tr, K, stake=None, coin_period=6, device=0, find_order=True):

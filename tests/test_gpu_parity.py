@@ -416,3 +416,31 @@ def test_native_ingest_orders_and_validates():
     r = e.results()
     r["new_c_per_call"] = ncs
     assert_same(o, r, what="ingested graph")
+
+
+# ---------------------------------------------------------------- several node-views per launch
+@pytest.mark.parametrize("M,N,K,B", [(4, 2000, 50, 5), (16, 30000, 4096, 8), (64, 40000, 8192, 3), (33, 9000, 1500, 40)])
+def test_batched_views_match_the_oracle(M, N, K, B):
+    """B independent node-views (own traces) advanced together by sw_batch_divide_rounds: every view equals the
+    oracle on its own trace and schedule (40 views need more than one cooperative launch at 33 members)."""
+    from swirld_b200 import engine, traces
+    from swirld_b200.traces import chunks
+    trs = [traces.gossip(M, N - 7 * v, 100 + v) for v in range(B)]       # ragged: the views differ in length
+    engs = [engine.Engine(M, tr.N) for tr in trs]
+    for e, tr in zip(engs, trs):
+        e.append_trace(tr)
+    ncs = [[] for _ in range(B)]
+    scheds = [list(chunks(tr.N, K)) for tr in trs]
+    for i in range(max(len(s) for s in scheds)):
+        live = [v for v in range(B) if i < len(scheds[v])]
+        engine.batch_divide_rounds([engs[v] for v in live], [scheds[v][i][0] for v in live], [scheds[v][i][1] for v in live])
+        for v in live:
+            nc = engs[v].decide_fame()
+            engs[v].find_order(nc)
+            ncs[v].append(sorted(nc))
+    for v in range(0, B, max(1, B // 6)):
+        o = orc.run_oracle(trs[v], K)
+        r = engs[v].results()
+        r["new_c_per_call"] = ncs[v]
+        assert_same(o, r, what="view %d of %d" % (v, B))
+        assert np.array_equal(o["oracle"].can_see(), engs[v].can_see())
