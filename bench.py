@@ -420,7 +420,7 @@ def bench_ours(args, wl, rank, world, local_rank):
         views_out = []
         Nv = min(N, args.views_events) if args.views_events else N
         for B in [int(x) for x in args.views.split(",")]:
-            trs = [make_trace(dict(wl, N=Nv), 1000 + 17 * rank + v) for v in range(B)]
+            trs = [make_trace(dict(wl, N=Nv, gen="gossip_np"), 1000 + 17 * rank + v) for v in range(B)]   # (vectorised generator: B traces)
             engs = [engine.Engine(M, Nv, device=local_rank) for _ in range(B)]
             for ev, tv in zip(engs, trs):
                 ev.append_trace(tv)
