@@ -293,13 +293,16 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     k_cs_heads<<<std::max(1, std::min(2 * e->n_sm, (int)(((size_t)(C.nb + 1) * M + 255) / 256))), 256, 0, st>>>(C);
     if (C.nb > 1) {
         k_cs_check<<<std::max(1, std::min(4 * e->n_sm, (int)(((size_t)C.nb * M + 7) / 8))), 256, 0, st>>>(C);
-        k_cs_slow<<<1, CS_SLOW_WARPS * 32, (size_t)CS_SLOW_WARPS * M * sizeof(int), st>>>(C);
+        const size_t ssm = (size_t)CS_SLOW_WARPS * M * sizeof(int);
+        k_cs_slow_wave<<<e->n_sm, CS_SLOW_WARPS * 32, ssm, st>>>(C, 1);
+        k_cs_slow_wave<<<e->n_sm, CS_SLOW_WARPS * 32, ssm, st>>>(C, 2);
+        k_cs_slow_rest<<<1, CS_SLOW_WARPS * 32, ssm, st>>>(C, 3);
     }
     k_cs_pass<2><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
     cudaEventRecord(b, st);
     e->spans.push_back(TimedSpan{a, b, 3});
     CK(cudaGetLastError());
-    e->stats.kernel_launches += C.nb > 1 ? 7 : 4;
+    e->stats.kernel_launches += C.nb > 1 ? 9 : 4;
     e->n_rowed = upto;
     return 0;
 }
@@ -539,7 +542,8 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         const size_t cs_smem = (size_t)M * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
         CK(cudaFuncSetAttribute(k_cs_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         CK(cudaFuncSetAttribute(k_cs_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
-        CK(cudaFuncSetAttribute(k_cs_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));
+        CK(cudaFuncSetAttribute(k_cs_slow_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));
+        CK(cudaFuncSetAttribute(k_cs_slow_rest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));
         return reset_state(e);
     }();
     if (rc < 0) { g_create_error = e->err; sw_destroy(e); return rc; }
@@ -903,32 +907,25 @@ int sw_find_order(sw_engine *e, const int32_t *new_c, int n) {
         k_order_list<<<std::max(1, std::min(4 * e->n_sm, (n * 64 + 255) / 256)), 256, 0, e->stream>>>(P);
     }
     CK(cudaGetLastError());
+    // the number of newly ordered events stays on the device: the time / sort kernels read it there, the host learns it
+    // from the one copy at the end of the call
+    if (e->wide) {
+        const size_t tsm = (size_t)OW_WARPS * M * sizeof(u64);
+        k_w_order_times<<<8 * e->n_sm, OW_WARPS * 32, tsm, e->stream>>>(P);
+    } else k_order_times<<<4 * e->n_sm, 256, 0, e->stream>>>(P);
+    k_order_sort<<<n, 1024, 0, e->stream>>>(P);
+    CK(cudaGetLastError());
+    cudaEventRecord(b, e->stream);
+    e->spans.push_back(TimedSpan{a, b, 2});
     CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));      // rs (host vector) was consumed by the copy above
-    e->stats.kernel_launches += 3;
+    CK(cudaStreamSynchronize(e->stream));      // (rs, the host vector of the rounds, was consumed by the copy above)
+    fold_spans(e);
+    e->stats.kernel_launches += 5;
     e->stats.h2d_bytes += sizeof(int32_t) * n;
     e->stats.d2h_bytes += sizeof(int32_t) * SC_COUNT;
     int rc = device_error(e);
-    const int nbatch = e->h_scal[SC_BATCH];
-    if (rc == 0 && nbatch > 0) {
-        if (e->wide) {
-            const size_t tsm = (size_t)OW_WARPS * M * sizeof(u64);
-            k_w_order_times<<<std::max(1, std::min(16 * e->n_sm, (nbatch + OW_WARPS - 1) / OW_WARPS)), OW_WARPS * 32, tsm, e->stream>>>(P, nbatch);
-        } else {
-            const int wpb = 8;
-            k_order_times<<<(nbatch + wpb - 1) / wpb, wpb * 32, 0, e->stream>>>(P, nbatch);
-        }
-        k_order_sort<<<n, 1024, 0, e->stream>>>(P);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(e->h_scal, e->d_scal, sizeof(int32_t) * SC_COUNT, cudaMemcpyDeviceToHost, e->stream));
-        e->stats.kernel_launches += 2;
-    }
-    cudaEventRecord(b, e->stream);
-    e->spans.push_back(TimedSpan{a, b, 2});
-    CK(cudaStreamSynchronize(e->stream));
-    fold_spans(e);
-    if (rc == 0) rc = device_error(e);
     if (rc < 0) return rc;
+    const int nbatch = e->h_scal[SC_BATCH];
     e->n_tx += nbatch;
     return nbatch;
 }

@@ -41,9 +41,9 @@ struct CsParams {
     int32_t *Qtab;              // [nb+1][M] head of member m at the start of block j
     int32_t *carry;             // [M] heads before `first` (in/out)
     int32_t *slow_list;         // [cap] the listed rows that failed the check (any order)
-    int32_t *slow_cnt;          // [4]: slow rows, (unused), rows on xlist; zero on entry
+    int32_t *slow_cnt;          // [4]: slow rows, slow rows still pending, rows on xlist; zero on entry
     int32_t *xlist;             // [cap] the rows a later block reads (each once)
-    uint8_t *sflag;             // [cap] 0 final, 1 pending slow row, 2 finished by k_cs_slow, 3 finished in the running wave
+    uint8_t *sflag;             // [cap] 0 final, 1 pending slow row, 2 + w finished in wave w of k_cs_slow_*
 };
 
 #define CS_TILE 128
@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(256) k_cs_check(CsParams P) {
         }
         if (!__all_sync(0xffffffffu, ok) && lane == 0) {
             P.slow_list[atomicAdd(&P.slow_cnt[0], 1)] = x;
+            atomicAdd(&P.slow_cnt[1], 1);
             P.sflag[x] = 1;
         }
     }
@@ -249,60 +250,68 @@ __global__ void __launch_bounds__(256) k_cs_check(CsParams P) {
 
 // The rows that failed the check: row(x)[c] = max(partial, max over members m of the FINAL row of the event through
 // which x enters m's chain below the block: the head Q[m] if x sees an in-block event of m (or the head itself),
-// else the direct out-of-block parent it shows).  Those events are listed rows of earlier blocks and nearly always
-// final already, so the rows are finished in waves: a row whose entry events are all final is finished now, the others
-// wait for the next wave (every wave finishes at least the pending rows of the lowest block).  One CTA; normally a
-// handful of rows, or none.
+// else the direct out-of-block parent it shows) -- for the columns that can still grow (neither in-block nor the head
+// itself).  Those entry events are listed rows of earlier blocks and nearly always final already, so the rows are
+// finished in dependency WAVES: a row whose entry events are all final (flag 0, or finished in an earlier wave) is
+// finished now and stamped 2 + wave, the others wait for the next wave; every wave finishes at least the pending rows
+// of the lowest block.  Waves 1 and 2 are grid-wide launches, whatever is left (normally nothing) is finished by one CTA.
 #define CS_SLOW_WARPS 16
-__global__ void __launch_bounds__(CS_SLOW_WARPS * 32) k_cs_slow(CsParams P) {
-    extern __shared__ int cs_smem[];
-    const int cnt = P.slow_cnt[0];
-    if (cnt == 0) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, M = P.M;
-    int *ent = cs_smem + (size_t)warp * M;                 // per warp: the entry event per member
-    __shared__ int left_s;
-    if (threadIdx.x == 0) left_s = cnt;
-    __syncthreads();
-    while (left_s > 0) {
-        for (int i = warp; i < cnt; i += CS_SLOW_WARPS) {
-            const int x = P.slow_list[i];
-            if (P.sflag[x] != 1) continue;
-            const int bx = cs_block_of(P, x), lim = cs_start(P, bx);
-            const int32_t *Q = P.Qtab + (size_t)bx * M;
-            bool ready = true;
-            for (int m = lane; m < M; m += 32) {
-                const int pr = P.row[(size_t)x * M + m], q = Q[m];
-                const int ev = (pr >= lim || pr == q) ? q : pr;
-                ent[m] = ev;
-                if (ev >= P.first) { const int f = P.sflag[ev]; ready &= !(f == 1 || f == 3); }
-            }
-            __syncwarp();
-            if (!__all_sync(0xffffffffu, ready)) continue;
-            // only the columns that are neither in-block nor the head itself can still grow: max over the entry events
-            for (int c0 = 0; c0 < M; c0 += 32) {
-                const int c = c0 + lane;
-                bool bad = false;
-                if (c < M) { const int pr = P.row[(size_t)x * M + c]; bad = pr < lim && pr != Q[c]; }
-                unsigned todo = __ballot_sync(0xffffffffu, bad);
-                while (todo) {
-                    const int cb = c0 + __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    int acc = -1;
-                    for (int m = lane; m < M; m += 32) {
-                        const int ev = ent[m];
-                        if (ev >= 0) acc = max(acc, __ldcg(P.row + (size_t)ev * M + cb));
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-                    if (lane == 0 && acc > P.row[(size_t)x * M + cb]) P.row[(size_t)x * M + cb] = acc;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) { P.sflag[x] = 3; atomicSub(&left_s, 1); }
+__device__ __forceinline__ int cs_slow_wave(const CsParams &P, int wave, int w0, int nwarps, int *ent, int lane) {
+    const int M = P.M, cnt = P.slow_cnt[0];
+    int done = 0;
+    for (int i = w0; i < cnt; i += nwarps) {
+        const int x = P.slow_list[i];
+        if (P.sflag[x] != 1) continue;
+        const int bx = cs_block_of(P, x), lim = cs_start(P, bx);
+        const int32_t *Q = P.Qtab + (size_t)bx * M;
+        bool ready = true;
+        for (int m = lane; m < M; m += 32) {
+            const int pr = P.row[(size_t)x * M + m], q = Q[m];
+            const int ev = (pr >= lim || pr == q) ? q : pr;
+            ent[m] = ev;
+            if (ev >= P.first) { const int f = P.sflag[ev]; ready &= f == 0 || (f >= 3 && f < 2 + wave); }
         }
+        __syncwarp();
+        if (!__all_sync(0xffffffffu, ready)) continue;
+        for (int c0 = 0; c0 < M; c0 += 32) {
+            const int c = c0 + lane;
+            bool bad = false;
+            if (c < M) { const int pr = P.row[(size_t)x * M + c]; bad = pr < lim && pr != Q[c]; }
+            unsigned todo = __ballot_sync(0xffffffffu, bad);
+            while (todo) {
+                const int cb = c0 + __ffs(todo) - 1;
+                todo &= todo - 1;
+                int acc = -1;
+                for (int m = lane; m < M; m += 32) {
+                    const int ev = ent[m];
+                    if (ev >= 0) acc = max(acc, __ldcg(P.row + (size_t)ev * M + cb));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+                if (lane == 0 && acc > P.row[(size_t)x * M + cb]) P.row[(size_t)x * M + cb] = acc;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { P.sflag[x] = (uint8_t)min(2 + wave, 250); atomicSub(&P.slow_cnt[1], 1); }
+        done++;
+    }
+    return done;
+}
+__global__ void __launch_bounds__(CS_SLOW_WARPS * 32) k_cs_slow_wave(CsParams P, int wave) {
+    extern __shared__ int cs_smem[];
+    if (P.slow_cnt[1] <= 0) return;
+    const int warp = threadIdx.x >> 5;
+    cs_slow_wave(P, wave, blockIdx.x * CS_SLOW_WARPS + warp, gridDim.x * CS_SLOW_WARPS, cs_smem + (size_t)warp * P.M, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(CS_SLOW_WARPS * 32) k_cs_slow_rest(CsParams P, int wave0) {
+    extern __shared__ int cs_smem[];
+    if (P.slow_cnt[1] <= 0) return;
+    const int warp = threadIdx.x >> 5;
+    for (int wave = wave0; wave < 248; wave++) {                 // (rows stamped in wave w count as final from wave w+1 on)
+        cs_slow_wave(P, wave, warp, CS_SLOW_WARPS, cs_smem + (size_t)warp * P.M, threadIdx.x & 31);
+        __threadfence_block();
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) { const int x = P.slow_list[i]; if (P.sflag[x] == 3) P.sflag[x] = 2; }
-        __syncthreads();
+        if (*(volatile int32_t *)&P.slow_cnt[1] <= 0) break;
     }
 }
 

@@ -463,11 +463,12 @@ __global__ void k_order_list(OrderParams P) {
 // walks down the witness's self-parent chain while the ancestor still sees x
 // (:298-302) and takes the timestamp of where it stops (the event before the first
 // seer, or the chain root -- quirk Q10); the lopsided median of :305 (quirk Q11).
-__global__ void __launch_bounds__(256) k_order_times(OrderParams P, int nbatch) {
+__global__ void __launch_bounds__(256) k_order_times(OrderParams P) {
     const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= nbatch) return;
+    const int nbatch = P.scal[SC_BATCH];                 // (left on the device by k_order_cuts: no host round trip)
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
     const int M = P.M;
+    for (int i = gw; i < nbatch; i += nw) {
     const int x = P.batch_ev[i], si = P.batch_seg[i];
     const int c = P.creator[x];
     const int nf = P.seg_nf[si];
@@ -519,6 +520,7 @@ __global__ void __launch_bounds__(256) k_order_times(OrderParams P, int nbatch) 
         for (int b = 0; b < 8; b++)
             kw = (kw << 8) | (u64)(P.seg_white[(size_t)si * 64 + 8 * lane + b] ^ P.sig[(size_t)x * 64 + 8 * lane + b]);
         P.key[(size_t)i * 8 + lane] = kw;
+    }
     }
 }
 

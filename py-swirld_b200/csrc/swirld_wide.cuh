@@ -856,8 +856,9 @@ __device__ __forceinline__ u64 warp_select(const u64 *keys, int n, int k, int la
 }
 
 #define OW_WARPS 4
-__global__ void __launch_bounds__(OW_WARPS * 32) k_w_order_times(OrderParams P, int nbatch) {
+__global__ void __launch_bounds__(OW_WARPS * 32) k_w_order_times(OrderParams P) {
     extern __shared__ u64 ot_smem[];
+    const int nbatch = P.scal[SC_BATCH];                 // (left on the device by k_w_order_cuts: no host round trip)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, M = P.M;
     u64 *keys = ot_smem + (size_t)warp * M;
     const int gw = blockIdx.x * OW_WARPS + warp, nw = gridDim.x * OW_WARPS;

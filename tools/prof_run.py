@@ -23,6 +23,7 @@ for p in range(passes):
     if p:
         e.rewind()
     s0 = e.stats()
+    e.debug_counters(clear=True)
     e.record(0)
     for first, cnt in chunks(N, K):
         e.divide_rounds(first, cnt)
@@ -30,5 +31,6 @@ for p in range(passes):
     e.record(1)
     ms = e.elapsed_ms(0, 1)
     s1 = e.stats()
-    out.append({"ms": round(ms, 3), "events_per_s": round(N / ms * 1e3), **{k: round(s1[k] - s0[k], 3) for k in s1 if k.startswith("ms_")}})
+    dbg = e.debug_counters(clear=True).tolist()
+    out.append({"dbg": dbg[:11], "ms": round(ms, 3), "events_per_s": round(N / ms * 1e3), **{k: round(s1[k] - s0[k], 3) for k in s1 if k.startswith("ms_")}})
 print(json.dumps({"M": M, "N": N, "K": K, "gen": gen, "gen_s": round(t_gen, 1), "max_round": e.max_round, "passes": out}))
