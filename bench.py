@@ -275,6 +275,58 @@ def workload_config(wl, world):
                   "table) also exceeds L2 from c3 up"}
 
 
+# --------------------------------------------------------------------------- streaming cadence
+def stream_leg(local_rank, cases=((4, 2000, 1), (4, 2000, 50), (64, 20000, 3))):
+    """The reference's own cadence: one (divide_rounds, decide_fame, find_order) triple per sync, a handful of events
+    per call (swirld.py:319-328).  Wall-clock through the C ABI -- sw_append + sw_divide_rounds (one launch:
+    k_stream_divide) + sw_decide_fame + sw_find_order per call, from host buffers -- next to the oracle port and the
+    unmodified Python reference on the SAME schedule (all three calls counted for every arm)."""
+    from swirld_b200 import engine, traces
+    from swirld_b200.traces import chunks
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    out = []
+    for M, N, K in cases:
+        tr = traces.gossip(M, N, 1)
+        o = orc.run_oracle(tr, K)
+        t_port = o["t_divide_rounds"] + o["t_decide_fame"] + o["t_find_order"]
+        best, res = None, None
+        for rep_i in range(3):
+            e = engine.Engine(M, N, device=local_rank)
+            e.sync()
+            t0 = time.perf_counter()
+            ncalls = 0
+            for first, cnt in chunks(N, K):
+                e.append_trace(tr, first, cnt)
+                e.divide_rounds(first, cnt)
+                e.find_order(e.decide_fame())
+                ncalls += 1
+            e.sync()
+            dt = time.perf_counter() - t0
+            if rep_i and (best is None or dt < best):
+                best = dt
+            res = e.results()
+            launches = e.stats()["kernel_launches"]
+            e.close()
+        same = all(np.array_equal(np.asarray(o[k]), np.asarray(res[k])) for k in ("round", "witness_table", "famous", "consensus", "transactions"))
+        pyref = None
+        ref = os.path.join(ROOT, "baseline", "_ref")
+        if os.path.isfile(os.path.join(ref, "swirld.py")):
+            os.environ["SWIRLD_REFERENCE"] = ref
+            try:
+                import ref_harness as rh
+                npre = min(N, 6000 if M >= 64 else 2000)
+                r = rh.run_reference(tr.slice(0, npre), K)
+                pyref = npre / (r["t_divide_rounds"] + r["t_decide_fame"] + r["t_find_order"])
+            except Exception as ex:
+                pyref = "unavailable: %s" % ex
+        out.append({"members": M, "events": N, "events_per_call": K, "calls": ncalls,
+                    "events_per_s": N / best, "us_per_call": 1e6 * best / ncalls, "kernel_launches_per_call": launches / ncalls,
+                    "port_events_per_s": N / t_port, "python_reference_events_per_s": pyref, "equals_oracle": bool(same)})
+        o["oracle"].close()
+    return out
+
+
 # --------------------------------------------------------------------------- multi-rank plumbing
 def rank_seed(rank, wl=None):
     """Replica workloads: every rank advances its own node-view (an independent trace).  Sharded workloads: all
@@ -592,6 +644,7 @@ def bench_ours(args, wl, rank, world, local_rank):
                 "ms": fo_ms, "cpu_port_events_per_s": n_cpu / fo_cpu if fo_cpu > 0 else None},
             "checksum": {"round_sum": check[0], "max_round": check[1], "consensus_rounds": check[2]},
             "views": views_out,
+            "stream": stream_leg(local_rank) if args.stream else None,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -609,6 +662,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--events", type=int, default=0, help="override the workload's event count")
     ap.add_argument("--no-find-order", action="store_true")
+    ap.add_argument("--stream", action="store_true", help="add the streaming-cadence leg (one sync per call)")
     ap.add_argument("--views", default="", help="comma list of view counts B for the multi-view leg (M <= 64), e.g. 1,8,32")
     ap.add_argument("--views-events", type=int, default=0, help="events per view in the multi-view leg (default: the workload's)")
     ap.add_argument("--no-python-reference", action="store_true")
