@@ -262,19 +262,28 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
         e->n_rowed = upto;
         return 0;
     }
-    // block length: >= 16 events per member and block, so that every member's last event of a block sees every
-    // block-start head (then the boundary check passes and nothing is left for the serial pass); SW_CS_B overrides
-    int B = std::max(e->cs_min_B, std::min(16 * M, 1 << 15));
+    // block length: >= 16 (32 above 64 members) events per member and block, so that nearly every member's last event of a
+    // block sees every block-start head (then the finality check passes; the rest goes through the waves); SW_CS_B overrides
+    int B = std::max(e->cs_min_B, std::min((M <= 64 ? 16 : 32) * M, 1 << 15));      // (above 64 members seeing every head takes more events per member)
     if (const char *v = getenv("SW_CS_B")) B = std::max(e->cs_min_B, atoi(v));
     B = (B + 3) & ~3;
     C.B = B;
     C.first_al = first & ~3;
     C.nb = (first + n <= C.first_al + B) ? 1 : 1 + (first + n - (C.first_al + B) + B - 1) / B;
     if (C.nb > 1 && first + n - (C.first_al + (C.nb - 1) * B) < 3 * B / 4) C.nb--;     // a short tail joins the block before it
-    // columns per tile: 32 (one warp = one 128-byte row segment), fewer when the (block, tile) pairs would not even
-    // put one warp on every scheduler -- the walk is a latency chain, narrower tiles buy parallel chains
+    // columns per tile: 32 (one warp = one 128-byte row segment) unless the per-member cache val[M][CT] then limits a
+    // SM to so few CTAs that narrower tiles finish in fewer waves (M = 1024: 128 KB per CTA at CT = 32)
     int CT = 32;
-    while (CT > 8 && (long long)C.nb * ((M + CT - 1) / CT) < 4LL * e->n_sm) CT >>= 1;
+    {
+        long long best = -1;
+        for (int ct = 32; ct >= 8; ct >>= 1) {
+            const long long smem_ct = (long long)M * ct * 4 + CS_TILE * 16 + CS_TILE;
+            const long long conc = std::max(1LL, std::min(32LL, (220LL << 10) / smem_ct));
+            const long long ctas = (long long)C.nb * ((M + ct - 1) / ct);
+            const long long waves = (ctas + e->n_sm * conc - 1) / (e->n_sm * conc);
+            if (best < 0 || waves < best) { best = waves; CT = ct; }
+        }
+    }
     if (const char *v = getenv("SW_CS_CT")) { const int x = atoi(v); if (x == 8 || x == 16 || x == 32) CT = x; }
     C.CT = CT;
     const int ntiles = (M + CT - 1) / CT;
@@ -384,8 +393,8 @@ int divide_rounds_wide(sw_engine *e, int first, int n) {
     const int grid = e->n_sm;
     const int nw = grid * (RW_THREADS / 32);
     const int nown = (M + e->nranks - 1) / e->nranks;
-    // events per member below a step's frontier: about two tests per warp and step, never more than half a window
-    R.L = std::max(1, std::min(RW_LMAX / 2, 2 * nw * e->nranks / std::max(1, M)));
+    // events per member below a step's frontier: about three tests per warp and step, never more than half a window
+    R.L = std::max(1, std::min(RW_LMAX / 2, 3 * nw * e->nranks / std::max(1, M)));
     (void)nown;
     if (const char *v = getenv("SW_RW_L")) R.L = std::max(1, std::min(RW_LMAX, atoi(v)));
     R.epoch = ++e->rb_epoch;
@@ -498,7 +507,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(dalloc(&e->d_p0, cap)); CK(dalloc(&e->d_p1, cap)); CK(dalloc(&e->d_creator, cap)); CK(dalloc(&e->d_seq, cap));
         CK(dalloc(&e->d_t, cap)); CK(dalloc(&e->d_sig, cap * 64)); CK(dalloc(&e->d_height, cap)); CK(dalloc(&e->d_stale, cap));
         // can_see scan scratch: per-event meta / flags / slow list, per-block tables (blocks are >= cs_min_B events)
-        e->cs_min_B = std::max(256, std::min(16 * M, 1 << 15));
+        e->cs_min_B = std::max(256, std::min((M <= 64 ? 16 : 32) * M, 1 << 15));
         if (const char *v = getenv("SW_CS_B")) e->cs_min_B = std::max(64, std::min(e->cs_min_B, atoi(v)));
         const size_t nbmax = cap / e->cs_min_B + 3;
         CK(dalloc(&e->d_cs_meta, cap)); CK(dalloc(&e->d_cs_wr, cap)); CK(dalloc(&e->d_cs_xb, cap)); CK(dalloc(&e->d_cs_slow, cap + 4));

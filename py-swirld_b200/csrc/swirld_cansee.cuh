@@ -251,10 +251,11 @@ __global__ void __launch_bounds__(256) k_cs_check(CsParams P) {
 // The rows that failed the check: row(x)[c] = max(partial, max over members m of the FINAL row of the event through
 // which x enters m's chain below the block: the head Q[m] if x sees an in-block event of m (or the head itself),
 // else the direct out-of-block parent it shows) -- for the columns that can still grow (neither in-block nor the head
-// itself).  Those entry events are listed rows of earlier blocks and nearly always final already, so the rows are
-// finished in dependency WAVES: a row whose entry events are all final (flag 0, or finished in an earlier wave) is
-// finished now and stamped 2 + wave, the others wait for the next wave; every wave finishes at least the pending rows
-// of the lowest block.  Waves 1 and 2 are grid-wide launches, whatever is left (normally nothing) is finished by one CTA.
+// itself).  Those entry events are listed rows of earlier blocks; their column in question is final unless the entry is
+// itself a row in flux AND that column is one of its open ones -- so the rows are finished in dependency WAVES, column
+// by column: an open column whose entries are all settled is written now; a row with no open column left is stamped
+// 2 + wave; the others wait for the next wave (the pending rows of the lowest block always finish).  Waves 1 and 2 are
+// grid-wide launches, whatever is left (normally nothing) is finished by one CTA.
 #define CS_SLOW_WARPS 16
 __device__ __forceinline__ int cs_slow_wave(const CsParams &P, int wave, int w0, int nwarps, int *ent, int lane) {
     const int M = P.M, cnt = P.slow_cnt[0];
@@ -264,15 +265,12 @@ __device__ __forceinline__ int cs_slow_wave(const CsParams &P, int wave, int w0,
         if (P.sflag[x] != 1) continue;
         const int bx = cs_block_of(P, x), lim = cs_start(P, bx);
         const int32_t *Q = P.Qtab + (size_t)bx * M;
-        bool ready = true;
         for (int m = lane; m < M; m += 32) {
             const int pr = P.row[(size_t)x * M + m], q = Q[m];
-            const int ev = (pr >= lim || pr == q) ? q : pr;
-            ent[m] = ev;
-            if (ev >= P.first) { const int f = P.sflag[ev]; ready &= f == 0 || (f >= 3 && f < 2 + wave); }
+            ent[m] = (pr >= lim || pr == q) ? q : pr;
         }
         __syncwarp();
-        if (!__all_sync(0xffffffffu, ready)) continue;
+        bool complete = true;
         for (int c0 = 0; c0 < M; c0 += 32) {
             const int c = c0 + lane;
             bool bad = false;
@@ -281,17 +279,32 @@ __device__ __forceinline__ int cs_slow_wave(const CsParams &P, int wave, int w0,
             while (todo) {
                 const int cb = c0 + __ffs(todo) - 1;
                 todo &= todo - 1;
+                // column cb of x = max over the entry events of THEIR column cb -- which is final unless the entry is
+                // itself a row in flux (pending, or finished in this very wave) whose column cb is one of its open ones
                 int acc = -1;
+                bool wait = false;
                 for (int m = lane; m < M; m += 32) {
                     const int ev = ent[m];
-                    if (ev >= 0) acc = max(acc, __ldcg(P.row + (size_t)ev * M + cb));
+                    if (ev < 0) continue;
+                    const int v = __ldcg(P.row + (size_t)ev * M + cb);
+                    acc = max(acc, v);
+                    if (ev >= P.first) {
+                        const int f = P.sflag[ev];
+                        if (f == 1 || f == min(2 + wave, 250)) {
+                            const int be = cs_block_of(P, ev);
+                            wait |= v < cs_start(P, be) && v != P.Qtab[(size_t)be * M + cb];
+                        }
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+                if (__any_sync(0xffffffffu, wait)) { complete = false; continue; }
                 if (lane == 0 && acc > P.row[(size_t)x * M + cb]) P.row[(size_t)x * M + cb] = acc;
             }
         }
         __syncwarp();
+        if (!complete) continue;                                 // some column waits for another row: next wave
+        __threadfence();
         if (lane == 0) { P.sflag[x] = (uint8_t)min(2 + wave, 250); atomicSub(&P.slow_cnt[1], 1); }
         done++;
     }

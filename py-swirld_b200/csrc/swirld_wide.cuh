@@ -235,11 +235,19 @@ __device__ __forceinline__ void rw_publish(const RwParams &P, int k, unsigned wo
     if (lane < NJ) P.scw[(size_t)k * NJ + lane] = word;
     if (fence) __threadfence();          // (not needed when a grid barrier separates the producers from the readers)
     __syncwarp();
-    if (lane == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(P.sctag + k), "l"(tag) : "memory");
+    if (lane == 0) {
+        if (fence) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(P.sctag + k), "l"(tag) : "memory");
+        else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(P.sctag + k), "l"(tag) : "memory");
+    }
 }
 __device__ __forceinline__ u64 rw_ld_tag(const u64 *p) {
     u64 v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 rw_ld_tag_relaxed(const u64 *p) {      // (the producer is a grid barrier away)
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -392,7 +400,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
                 if (len[c] > 0 && sq >= cmin_s[c]) k = P.cev[off[c] + sq - cmin_s[c]];
                 else k = __ldcg(P.gchain + (size_t)c * RW_RING + (sq & (RW_RING - 1)));
                 if (k < 0) continue;
-                if (rw_ld_tag(P.sctag + k) == tag) continue;          // prepared by an earlier launch step of this round
+                if (rw_ld_tag_relaxed(P.sctag + k) == tag) continue;  // prepared by an earlier step of this round
                 const unsigned word = seen_words<NJ>(P.row + (size_t)k * M, Wc, M, lane);
                 rw_publish<NJ>(P, k, word, tag, lane, false);
             }

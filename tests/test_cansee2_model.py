@@ -97,27 +97,42 @@ def scan_launch(tr, stale, first, n, B, row, carry, stats):
                 stats["fast"] += 1
             else:
                 slow[j].append(x)
-    # in dependency waves: a row is finished when every event it enters the lower blocks through is final
+    # in dependency waves, column by column: an open column (neither in-block nor the head itself) of a pending row is the
+    # max over the row's entry events of THEIR column -- final unless the entry is itself a row in flux whose column is open
     pending = {x: j for j in range(nb) for x in slow[j]}
+
+    def open_cols(x, j):
+        pr = row[x]
+        return (pr < starts[j]) & (pr != Q[j])
     while pending:
-        snapshot = set(pending)
-        done_now = []
-        for x, j in pending.items():
+        flux = dict(pending)                         # pending, or finished in this very wave
+        finished = []
+        progress = False
+        for x, j in list(pending.items()):
             pr = row[x].copy()
             inb = pr >= starts[j]
             ent = [Q[j, m] if (inb[m] or pr[m] == Q[j, m]) else pr[m] for m in range(M)]
-            if any(e in snapshot for e in ent):
-                continue
-            stats["slow"] += 1
-            acc = pr.copy()
-            for e in ent:
-                if e >= 0:
+            complete = True
+            for cb in np.nonzero(open_cols(x, j))[0]:
+                wait, acc = False, -1
+                for e in ent:
+                    if e < 0:
+                        continue
                     assert e < starts[j]
-                    acc = np.maximum(acc, row[e])
-            done_now.append((x, np.where(inb, pr, acc)))
-        assert done_now, "a wave must finish at least the lowest block's rows"
-        for x, v in done_now:                       # (rows finished in a wave are not read in the same wave)
-            row[x] = v
+                    acc = max(acc, row[e][cb])
+                    if e in flux and open_cols(e, flux[e])[cb]:
+                        wait = True
+                if wait:
+                    complete = False
+                    continue
+                if acc > row[x][cb]:
+                    row[x][cb] = acc
+                    progress = True
+            if complete:
+                finished.append(x)
+        assert finished, "a wave must finish at least the lowest block's rows"
+        for x in finished:
+            stats["slow"] += 1
             del pending[x]
         stats["waves"] = stats.get("waves", 0) + 1
     # ---- pass 2: the exact rows; out-of-block parents contribute their final rows
