@@ -22,7 +22,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cases = [("gossip", 96, 20000, 3000), ("adversarial", 130, 30000, 8192), ("gossip_np", 256, 120000, 40000), ("gossip_np", 1024, 60000, 30000)]
+    cases = [("gossip", 96, 20000, 3000), ("adversarial", 130, 30000, 8192), ("gossip_np", 256, 120000, 40000), ("gossip_np", 1024, 24000, 12000)]
     for gen, M, N, K in cases:
         tr = getattr(traces, gen)(M, N, 7)
         e = engine.Engine(M, N, device=local)
