@@ -277,7 +277,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     {
         long long best = -1;
         for (int ct = 32; ct >= 8; ct >>= 1) {
-            const long long smem_ct = (long long)M * ct * 4 + CS_TILE * 16 + CS_TILE;
+            const long long smem_ct = (long long)(M + CS_TILE) * ct * 4 + CS_TILE * 16 + 2 * CS_TILE;
             const long long conc = std::max(1LL, std::min(32LL, (220LL << 10) / smem_ct));
             const long long ctas = (long long)C.nb * ((M + ct - 1) / ct);
             const long long waves = (ctas + e->n_sm * conc - 1) / (e->n_sm * conc);
@@ -287,7 +287,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     if (const char *v = getenv("SW_CS_CT")) { const int x = atoi(v); if (x == 8 || x == 16 || x == 32) CT = x; }
     C.CT = CT;
     const int ntiles = (M + CT - 1) / CT;
-    const size_t smem = (size_t)M * CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
+    const size_t smem = (size_t)(M + CS_TILE) * CT * sizeof(int) + CS_TILE * sizeof(int4) + 2 * CS_TILE;
     const int pblocks = std::max(1, std::min(8 * e->n_sm, (n + 255) / 256));
     k_fill_i32<<<std::max(1, std::min(256, (int)(((size_t)C.nb * M + 255) / 256))), 256, 0, st>>>(e->d_cs_last, -1, (size_t)C.nb * M);
     if (C.nb > 1) {
@@ -548,7 +548,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(cudaMallocHost((void **)&e->h_newc, sizeof(int32_t) * e->Rcap));
         CK(cudaMemcpyAsync(e->d_stake, e->h_stake.data(), sizeof(i64) * M, cudaMemcpyHostToDevice, e->stream));
         // kernels that need more than the default 48 KB of dynamic shared memory
-        const size_t cs_smem = (size_t)M * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + CS_TILE;
+        const size_t cs_smem = (size_t)(M + CS_TILE) * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + 2 * CS_TILE;
         CK(cudaFuncSetAttribute(k_cs_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         CK(cudaFuncSetAttribute(k_cs_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         CK(cudaFuncSetAttribute(k_cs_slow_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));

@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     const int CT = P.CT;
     int4 *meta = reinterpret_cast<int4 *>(cs_smem);                                // [CS_TILE]
     uint8_t *wrt = reinterpret_cast<uint8_t *>(meta + CS_TILE);                    // [CS_TILE]
-    int *valb = cs_smem + CS_TILE * 4 + CS_TILE / 4;                               // [M][CT]
+    uint8_t *slist = wrt + CS_TILE;                                                // [CS_TILE] tile positions of the prefetched stale parents
+    int *svb = cs_smem + CS_TILE * 4 + CS_TILE / 2;                                // [CS_TILE][CT] prefetched rows of stale other-parents
+    int *valb = svb + CS_TILE * CT;                                                // [M][CT]
     const int tl = threadIdx.x, M = P.M, blk = blockIdx.x;
     const int lane = tl & (CT - 1);                                                // lanes >= CT shadow lane % CT (their stores are off)
     const int c = blockIdx.y * CT + lane;
@@ -137,6 +139,32 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
             if (PASS == 1) wrt[i] = P.wr[t0 + i];
         }
         __syncwarp();
+        // a stale other-parent (not its member's latest event) is read from the table; when it lies before this tile its
+        // value is there already: fetch all of the tile's now, eight loads in flight, instead of one memory round trip
+        // per event in the walk
+        {
+            int ns = 0;
+            for (int i0 = 0; i0 < tn; i0 += CS_CT) {
+                const int i = i0 + tl;
+                bool pf = false;
+                if (i < tn) { const int4 mi = meta[i]; pf = ((mi.z >> 16) & 1) && mi.y < t0 && (PASS == 2 || mi.y >= s); }
+                const unsigned bal = __ballot_sync(0xffffffffu, pf);
+                if (pf) slist[ns + __popc(bal & ((1u << tl) - 1))] = (uint8_t)i;
+                ns += __popc(bal);
+            }
+            __syncwarp();
+            for (int k0 = 0; k0 < ns; k0 += 8) {
+                int v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = slist[min(k0 + u, ns - 1)];
+                    v[u] = col ? rowc[(size_t)meta[i].y * M] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (k0 + u < ns && own) svb[slist[k0 + u] * CT + lane] = v[u];
+            }
+        }
         int i = 0;
         while (i < tn) {
             const int4 m0 = meta[i];
@@ -178,11 +206,11 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 int x, y;
                 if (PASS == 1) {
                     x = a >= s ? val(cr)[lane] : -1;
-                    if (b >= s) y = st ? (col ? rowc[(size_t)b * M] : -1) : val(cb)[lane];
+                    if (b >= s) y = st ? (b < t0 ? svb[i * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane];
                     else y = (b >= 0 && c == cb) ? b : -1;
                 } else {
                     x = val(cr)[lane];
-                    y = b < 0 ? -1 : (st ? (col ? rowc[(size_t)b * M] : -1) : val(cb)[lane]);
+                    y = b < 0 ? -1 : (st ? (b < t0 ? svb[i * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane]);
                 }
                 const int v = c == cr ? h : max(x, y);
                 if (own) val(cr)[lane] = v;
