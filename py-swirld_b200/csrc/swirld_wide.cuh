@@ -138,12 +138,14 @@ __device__ __forceinline__ unsigned vcount_gt(const int *ev, int M, const unsign
 template <int NJ>
 __device__ __forceinline__ unsigned seen_words(const int32_t *__restrict__ rowk, const int *Wc, int M, int lane) {
     unsigned mine = 0;
+    int v[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) v[j] = lane + 32 * j < M ? __ldcg(rowk + lane + 32 * j) : -1;      // the whole row in flight at once
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
         const int c = lane + 32 * j;
-        bool bit = false;
-        if (c < M) { const int wv = Wc[c]; bit = wv >= 0 && __ldcg(rowk + c) >= wv; }
-        const unsigned b = __ballot_sync(0xffffffffu, bit);
+        const int wv = c < M ? Wc[c] : -1;
+        const unsigned b = __ballot_sync(0xffffffffu, wv >= 0 && v[j] >= wv);
         if (lane == j) mine = b;
     }
     return mine;
@@ -426,12 +428,17 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k_rounds_wide(RwParams P) {
                 if (tpa < 0) continue;                                  // a root is never promoted
                 i64 lv = 0;
                 __syncwarp();
-                for (int c0 = 0; c0 < M; c0 += 32) {
-                    const int c = c0 + lane;
+                int rv[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; j++) rv[j] = lane + 32 * j < M ? __ldcg(P.row + (size_t)th * M + lane + 32 * j) : -1;   // the row in flight at once
+#pragma unroll
+                for (int j = 0; j < NJ; j++) {
+                    const int c = lane + 32 * j;
+                    if (32 * j >= M) break;
                     int v = -1;
                     bool live = false;
                     if (c < M) {
-                        v = c == tc ? tpa : __ldcg(P.row + (size_t)th * M + c);
+                        v = c == tc ? tpa : rv[j];
                         const int wv = Wc[c];
                         live = wv >= 0 && v >= wv;
                         spre[c] = live ? v : -1;
@@ -557,12 +564,16 @@ __global__ void __launch_bounds__(256) k_w_seenmask(int M, int first, int n, int
         unsigned mine = 0;
         if (r >= 0 && r < Rcap) {
             const int32_t *Wr = W + (size_t)r * M;
+            int v[NJ], w[NJ];
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
                 const int c = lane + 32 * j;
-                bool bit = false;
-                if (c < M) { const int w = Wr[c]; bit = w >= 0 && row[(size_t)h * M + c] >= w; }
-                const unsigned b = __ballot_sync(0xffffffffu, bit);
+                v[j] = c < M ? row[(size_t)h * M + c] : -1;
+                w[j] = c < M ? Wr[c] : -1;
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+                const unsigned b = __ballot_sync(0xffffffffu, w[j] >= 0 && v[j] >= w[j]);
                 if (lane == j) mine = b;
             }
         }
@@ -591,9 +602,14 @@ __global__ void __launch_bounds__(256) k_w_strong(StrongParams P) {
         if (rh < 1) continue;
         const int r = rh - 1;
         __syncwarp();
-        for (int c = lane; c < M; c += 32) {
-            const int k = P.row[(size_t)h * M + c];
-            ev[c] = (k >= 0 && P.round[k] == r) ? k : -1;
+        {
+            int k[NJ], rk[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; j++) k[j] = lane + 32 * j < M ? P.row[(size_t)h * M + lane + 32 * j] : -1;
+#pragma unroll
+            for (int j = 0; j < NJ; j++) rk[j] = k[j] >= 0 ? P.round[k[j]] : -1;
+#pragma unroll
+            for (int j = 0; j < NJ; j++) if (lane + 32 * j < M) ev[lane + 32 * j] = (k[j] >= 0 && rk[j] == r) ? k[j] : -1;
         }
         __syncwarp();
         const unsigned gt = vcount_gt<NJ>(ev, M, P.SMw, P.tot2 / 3, P.unit != 0, stake_s, lane);
