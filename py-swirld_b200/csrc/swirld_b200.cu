@@ -450,7 +450,8 @@ int divide_rounds_wide(sw_engine *e, int first, int n) {
 template <int NJ>
 int fame_rounds_wide(sw_engine *e, const FameParams &P) {
     const size_t smem = (size_t)(32 * NJ + 64) * sizeof(int) + (size_t)(32 + e->M) * sizeof(i64);
-    k_w_fame_rounds<NJ><<<2 * e->n_sm, 1024, smem, e->stream>>>(P);
+    const int parts = (e->M + FW_THREADS - 1) / FW_THREADS;
+    k_w_fame_rounds<NJ><<<(2 * e->n_sm / parts + 1) * parts, FW_THREADS, smem, e->stream>>>(P);
     return 0;
 }
 

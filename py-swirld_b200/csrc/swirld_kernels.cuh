@@ -172,6 +172,9 @@ __global__ void k_fame_begin(FameParams P) {                    // one warp
         mc += 32;
     }
     if (lane == 0) { P.scal[SC_MAXC] = min(mc, P.Rcap); P.scal[SC_NEWC] = 0; }
+    // the open rounds' tallies (the wide kernel adds them up from several CTAs per round)
+    const int max_r = P.scal[SC_MAX_ROUND];
+    for (int r = min(mc, P.Rcap) + lane; r <= max_r && r < P.Rcap; r += 32) { P.rem[r] = 0; P.done[r] = 0; }
 }
 
 __global__ void __launch_bounds__(256) k_fame_rounds(FameParams P) {

@@ -630,21 +630,25 @@ __device__ __forceinline__ i64 w_wsum(const unsigned (&m)[NJ], bool unit, const 
     return s;
 }
 
-// One CTA per candidate round r, one THREAD per witness x = (r, mx): its vote mask over the voters of the
-// previous voter round (NJ words) stays in registers; the voters' sets S[r_][m] are staged 32 voters at a time.
+// One THREAD per witness x = (r, mx): its vote mask over the voters of the previous voter round (NJ words) stays in
+// registers; the voters' sets S[r_][m] are staged 32 voters at a time.  A candidate round r is spread over
+// ceil(M / FW_THREADS) CTAs (the witnesses are independent recurrences); they add up rem[r] / done[r], which
+// k_fame_begin cleared.
+#define FW_THREADS 256
 template <int NJ>
-__global__ void __launch_bounds__(1024) k_w_fame_rounds(FameParams P) {
+__global__ void __launch_bounds__(FW_THREADS) k_w_fame_rounds(FameParams P) {
     extern __shared__ int fw_smem[];
     unsigned *sS = reinterpret_cast<unsigned *>(fw_smem);            // [32][NJ] staged voter sets
     int *vw = fw_smem + 32 * NJ;                                     // [32] voter present
     int *vcoin = vw + 32;                                            // [32]
     i64 *vsum = reinterpret_cast<i64 *>(vcoin + 32);                 // [32] stake of the voter's set
     i64 *stake_s = vsum + 32;                                        // [M]
-    const int tid = threadIdx.x, M = P.M, mx = tid;
+    const int tid = threadIdx.x, M = P.M;
+    const int parts = (M + FW_THREADS - 1) / FW_THREADS, mx = (blockIdx.x % parts) * FW_THREADS + tid;
     const bool unit = P.unit != 0;
     const int max_r = P.scal[SC_MAX_ROUND], max_c = P.scal[SC_MAXC];
     for (int c = tid; c < M; c += blockDim.x) stake_s[c] = P.stake[c];
-    for (int r = max_c + blockIdx.x; r <= max_r; r += gridDim.x) {
+    for (int r = max_c + blockIdx.x / parts; r <= max_r; r += gridDim.x / parts) {
         __syncthreads();
         const size_t slot = (size_t)r * M + mx;
         int x = -1;
@@ -717,7 +721,7 @@ __global__ void __launch_bounds__(1024) k_w_fame_rounds(FameParams P) {
         }
         const int left = __syncthreads_count(live);
         const int dn = __syncthreads_or(any_decided);
-        if (tid == 0) { P.rem[r] = left; P.done[r] = dn ? 1 : 0; }
+        if (tid == 0) { if (left) atomicAdd(&P.rem[r], left); if (dn) P.done[r] = 1; }
     }
 }
 
