@@ -164,10 +164,25 @@ class GpuConsensus:
         self._pending = []
 
     def _grow(self, need):
-        """A bigger engine, fed the same events and the same call schedule (the final order depends on it)."""
+        """A bigger engine that continues where this one stands: through a checkpoint (sw_save / sw_load with a larger
+        capacity) where the engine has one, else by feeding the same events and the same call schedule again (the
+        final order depends on the schedule)."""
         while self._capacity < need:
             self._capacity *= 2
-        old, self._eng = self._eng, self._make_engine(self._capacity)
+        old = self._eng
+        if hasattr(old, "save"):
+            import os
+            import tempfile
+            fd, path = tempfile.mkstemp(suffix=".swb")
+            os.close(fd)
+            try:
+                old.save(path)
+                self._eng = type(old).load(path, device=self._device, capacity=self._capacity)
+            finally:
+                os.unlink(path)
+            old.close()
+            return
+        self._eng = self._make_engine(self._capacity)
         if self._n_on_device:
             self._eng.append(*self._columns(range(self._n_on_device)))
         for op in self._ops:
