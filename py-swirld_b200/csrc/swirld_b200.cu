@@ -277,7 +277,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     {
         long long best = -1;
         for (int ct = 32; ct >= 8; ct >>= 1) {
-            const long long smem_ct = (long long)(M + CS_TILE) * ct * 4 + CS_TILE * 16 + 2 * CS_TILE;
+            const long long smem_ct = (long long)(M + CS_SV) * ct * 4 + CS_TILE * 16 + 3 * CS_TILE;
             const long long conc = std::max(1LL, std::min(32LL, (220LL << 10) / smem_ct));
             const long long ctas = (long long)C.nb * ((M + ct - 1) / ct);
             const long long waves = (ctas + e->n_sm * conc - 1) / (e->n_sm * conc);
@@ -287,7 +287,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     if (const char *v = getenv("SW_CS_CT")) { const int x = atoi(v); if (x == 8 || x == 16 || x == 32) CT = x; }
     C.CT = CT;
     const int ntiles = (M + CT - 1) / CT;
-    const size_t smem = (size_t)(M + CS_TILE) * CT * sizeof(int) + CS_TILE * sizeof(int4) + 2 * CS_TILE;
+    const size_t smem = (size_t)(M + CS_SV) * CT * sizeof(int) + CS_TILE * sizeof(int4) + 3 * CS_TILE;
     const int pblocks = std::max(1, std::min(8 * e->n_sm, (n + 255) / 256));
     k_fill_i32<<<std::max(1, std::min(256, (int)(((size_t)C.nb * M + 255) / 256))), 256, 0, st>>>(e->d_cs_last, -1, (size_t)C.nb * M);
     if (C.nb > 1) {
@@ -318,10 +318,10 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
 
 // rounds of the chunk by the cooperative round-batch kernel (swirld_rounds.cuh), M <= 64: parameters + the kernels
 // that group the chunk's events by creator (`grid` = CTAs this view's round kernel will run on)
-int round_batch_prep(sw_engine *e, int first, int n, int grid, RbParams &R) {
+int round_batch_prep(sw_engine *e, int first, int n, int grid, RbParams &R, int min_L = 1) {
     R = RbParams{};
     R.M = e->M; R.first = first; R.n = n; R.Rcap = e->Rcap;
-    R.L = std::max(1, std::min(RB_LMAX, grid * (RB_THREADS / 32) / e->M));
+    R.L = std::max(std::min(min_L, RB_LMAX), std::min(RB_LMAX, grid * (RB_THREADS / 32) / e->M));
     R.maxmiss = RB_MAXMISS;
     R.epoch = ++e->rb_epoch;
     if (const char *v = getenv("SW_RB_L")) R.L = std::max(1, std::min(R.L, atoi(v)));          // tuning knobs
@@ -549,7 +549,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(cudaMallocHost((void **)&e->h_newc, sizeof(int32_t) * e->Rcap));
         CK(cudaMemcpyAsync(e->d_stake, e->h_stake.data(), sizeof(i64) * M, cudaMemcpyHostToDevice, e->stream));
         // kernels that need more than the default 48 KB of dynamic shared memory
-        const size_t cs_smem = (size_t)(M + CS_TILE) * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + 2 * CS_TILE;
+        const size_t cs_smem = (size_t)(M + CS_SV) * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + 3 * CS_TILE;
         CK(cudaFuncSetAttribute(k_cs_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         CK(cudaFuncSetAttribute(k_cs_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         CK(cudaFuncSetAttribute(k_cs_slow_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));
@@ -789,7 +789,7 @@ int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, c
             return fail(e, SW_E_ARG, "sw_batch_divide_rounds: view %d: bad range [%d,%d)", v, first[v], first[v] + n[v]);
     }
     CK(cudaSetDevice(e->device));
-    const int M = e->M, gmin = (M + RB_THREADS / 32 - 1) / (RB_THREADS / 32);    // a view needs one warp per member chain
+    const int gmin = 1;                                     // (a view's warps loop over its (chain, position) pairs)
     const int per_launch = std::max(1, e->n_sm / gmin);
     if (B > e->views_cap) {
         if (e->d_views) cudaFree(e->d_views);
@@ -809,7 +809,8 @@ int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, c
                 CK(cudaEventRecord(x->scan_ev, x->stream));
                 x->scan_ev_set = true;
             } else if (wait_appends(x, first[v] + n[v]) < 0) return SW_E_CUDA;
-            if (round_batch_prep(x, first[v], n[v], G, Rv[v]) < 0) { e->err = x->err; return SW_E_CUDA; }
+            // a view's window stays a round deep (16 pending events per chain) however few warps it has: they loop
+            if (round_batch_prep(x, first[v], n[v], G, Rv[v], 16) < 0) { e->err = x->err; return SW_E_CUDA; }
             cudaEvent_t ev = get_event(x);
             CK(cudaEventRecord(ev, x->stream));
             CK(cudaStreamWaitEvent(e->stream, ev, 0));

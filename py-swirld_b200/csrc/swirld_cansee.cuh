@@ -47,6 +47,7 @@ struct CsParams {
 };
 
 #define CS_TILE 128
+#define CS_SV 32                // prefetch slots for the stale other-parents of a tile (the rest is read in the walk)
 #define CS_CT 32                // threads per CTA (one warp); columns per tile = P.CT <= 32
 
 // (the last block takes whatever is left: a short tail block would fail the finality check often, so the host
@@ -80,20 +81,24 @@ __global__ void __launch_bounds__(256) k_cs_prep(CsParams P) {
         } else atomicMax(&P.last[c], h);
         int clean = 0;
         if ((h & 3) == 0 && h + 3 < cs_end(P, bh)) {       // h, h+1, h+2, h+3: no member written by one is read by a later one
-            int cr[4], co[4];
-            bool ok = st == 0;
-            cr[0] = c; co[0] = b >= 0 ? cb : c;
+            // (a stale other-parent is read from the table, not from the cache: it takes part when it lies before the
+            //  group's tile, where the walk prefetches it)
+            const int s0 = cs_start(P, bh), t0 = s0 + ((h - s0) / CS_TILE) * CS_TILE;
+            int cr[4], co[4], sti[4];
+            cr[0] = c; co[0] = b >= 0 ? cb : c; sti[0] = st;
+            bool ok = !st || b < t0;
 #pragma unroll
             for (int i = 1; i < 4; i++) {
                 const int bi = P.p1[h + i];
                 cr[i] = P.creator[h + i];
                 co[i] = bi >= 0 ? P.creator[bi] : cr[i];
-                ok &= !(bi >= 0 && P.stale[h + i]);
+                sti[i] = (bi >= 0 && P.stale[h + i]) ? 1 : 0;
+                ok &= !sti[i] || bi < t0;
             }
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = i + 1; j < 4; j++) ok &= cr[i] != cr[j] && cr[i] != co[j];
+                for (int j = i + 1; j < 4; j++) ok &= cr[i] != cr[j] && (sti[j] || cr[i] != co[j]);
             clean = ok ? 1 : 0;
         }
         P.meta[h] = make_int4(a, b, c | (st << 16) | (clean << 17), cb);
@@ -107,9 +112,10 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     const int CT = P.CT;
     int4 *meta = reinterpret_cast<int4 *>(cs_smem);                                // [CS_TILE]
     uint8_t *wrt = reinterpret_cast<uint8_t *>(meta + CS_TILE);                    // [CS_TILE]
-    uint8_t *slist = wrt + CS_TILE;                                                // [CS_TILE] tile positions of the prefetched stale parents
-    int *svb = cs_smem + CS_TILE * 4 + CS_TILE / 2;                                // [CS_TILE][CT] prefetched rows of stale other-parents
-    int *valb = svb + CS_TILE * CT;                                                // [M][CT]
+    uint8_t *slist = wrt + CS_TILE;                                                // [CS_SV] tile positions of the prefetched stale parents
+    uint8_t *sslot = slist + CS_TILE;                                              // [CS_TILE] tile position -> prefetch slot, 255 none
+    int *svb = cs_smem + CS_TILE * 4 + 3 * CS_TILE / 4;                            // [CS_SV][CT] prefetched rows of stale other-parents
+    int *valb = svb + CS_SV * CT;                                                  // [M][CT]
     const int tl = threadIdx.x, M = P.M, blk = blockIdx.x;
     const int lane = tl & (CT - 1);                                                // lanes >= CT shadow lane % CT (their stores are off)
     const int c = blockIdx.y * CT + lane;
@@ -149,9 +155,12 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 bool pf = false;
                 if (i < tn) { const int4 mi = meta[i]; pf = ((mi.z >> 16) & 1) && mi.y < t0 && (PASS == 2 || mi.y >= s); }
                 const unsigned bal = __ballot_sync(0xffffffffu, pf);
-                if (pf) slist[ns + __popc(bal & ((1u << tl) - 1))] = (uint8_t)i;
+                const int slot = ns + __popc(bal & ((1u << tl) - 1));
+                if (i < tn) sslot[i] = (pf && slot < CS_SV) ? (uint8_t)slot : (uint8_t)255;
+                if (pf && slot < CS_SV) slist[slot] = (uint8_t)i;
                 ns += __popc(bal);
             }
+            ns = min(ns, CS_SV);
             __syncwarp();
             for (int k0 = 0; k0 < ns; k0 += 8) {
                 int v[8];
@@ -162,30 +171,42 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 }
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (k0 + u < ns && own) svb[slist[k0 + u] * CT + lane] = v[u];
+                    if (k0 + u < ns && own) svb[(k0 + u) * CT + lane] = v[u];
             }
         }
         int i = 0;
         while (i < tn) {
             const int4 m0 = meta[i];
             const int h = t0 + i;
-            if (((m0.z >> 17) & 1) && i + 4 <= tn) {
-                // four events with pairwise disjoint members, none stale: all cache reads first
+            bool fast = ((m0.z >> 17) & 1) && i + 4 <= tn;
+            if (fast) {                                    // (a stale member of the group needs its prefetch slot)
+                const unsigned stm = ((m0.z >> 16) & 1) | (((meta[i + 1].z >> 16) & 1) << 1) | (((meta[i + 2].z >> 16) & 1) << 2) | (((meta[i + 3].z >> 16) & 1) << 3);
+                if (stm) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (((stm >> u) & 1) && !(PASS == 1 && meta[i + u].y < s) && sslot[i + u] == 255) fast = false;
+                }
+            }
+            if (fast) {
+                // four events with pairwise disjoint members: all cache reads first
                 const int4 m1 = meta[i + 1], m2 = meta[i + 2], m3 = meta[i + 3];
                 const int c0 = m0.z & 0xffff, c1 = m1.z & 0xffff, c2 = m2.z & 0xffff, c3 = m3.z & 0xffff;
                 int x0, x1, x2, x3, y0, y1, y2, y3;
+                auto other = [&](const int4 &m, int k) -> int {      // the other-parent's contribution in this column
+                    if ((m.z >> 16) & 1) {
+                        if (PASS == 1 && m.y < s) return (c == m.w) ? m.y : -1;
+                        return svb[sslot[i + k] * CT + lane];
+                    }
+                    if (PASS == 1) return m.y >= s ? val(m.w)[lane] : ((m.y >= 0 && c == m.w) ? m.y : -1);
+                    return m.y >= 0 ? val(m.w)[lane] : -1;
+                };
                 if (PASS == 1) {
                     x0 = m0.x >= s ? val(c0)[lane] : -1; x1 = m1.x >= s ? val(c1)[lane] : -1;
                     x2 = m2.x >= s ? val(c2)[lane] : -1; x3 = m3.x >= s ? val(c3)[lane] : -1;
-                    y0 = m0.y >= s ? val(m0.w)[lane] : ((m0.y >= 0 && c == m0.w) ? m0.y : -1);
-                    y1 = m1.y >= s ? val(m1.w)[lane] : ((m1.y >= 0 && c == m1.w) ? m1.y : -1);
-                    y2 = m2.y >= s ? val(m2.w)[lane] : ((m2.y >= 0 && c == m2.w) ? m2.y : -1);
-                    y3 = m3.y >= s ? val(m3.w)[lane] : ((m3.y >= 0 && c == m3.w) ? m3.y : -1);
                 } else {
                     x0 = val(c0)[lane]; x1 = val(c1)[lane]; x2 = val(c2)[lane]; x3 = val(c3)[lane];
-                    y0 = m0.y >= 0 ? val(m0.w)[lane] : -1; y1 = m1.y >= 0 ? val(m1.w)[lane] : -1;
-                    y2 = m2.y >= 0 ? val(m2.w)[lane] : -1; y3 = m3.y >= 0 ? val(m3.w)[lane] : -1;
                 }
+                y0 = other(m0, 0); y1 = other(m1, 1); y2 = other(m2, 2); y3 = other(m3, 3);
                 const int v0 = c == c0 ? h : max(x0, y0), v1 = c == c1 ? h + 1 : max(x1, y1);
                 const int v2 = c == c2 ? h + 2 : max(x2, y2), v3 = c == c3 ? h + 3 : max(x3, y3);
                 if (own) { val(c0)[lane] = v0; val(c1)[lane] = v1; val(c2)[lane] = v2; val(c3)[lane] = v3; }
@@ -206,11 +227,11 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 int x, y;
                 if (PASS == 1) {
                     x = a >= s ? val(cr)[lane] : -1;
-                    if (b >= s) y = st ? (b < t0 ? svb[i * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane];
+                    if (b >= s) y = st ? (sslot[i] != 255 ? svb[sslot[i] * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane];
                     else y = (b >= 0 && c == cb) ? b : -1;
                 } else {
                     x = val(cr)[lane];
-                    y = b < 0 ? -1 : (st ? (b < t0 ? svb[i * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane]);
+                    y = b < 0 ? -1 : (st ? (sslot[i] != 255 ? svb[sslot[i] * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane]);
                 }
                 const int v = c == cr ? h : max(x, y);
                 if (own) val(cr)[lane] = v;

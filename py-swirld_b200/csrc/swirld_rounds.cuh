@@ -323,7 +323,7 @@ __device__ __forceinline__ void rounds_batch_body(const RbParams &P, const int b
         if (rmin == 0x7fffffff) break;                        // every chain is done
         const int buf = step % 3;
         // ---- this warp's test of the step: fetch its inputs now, they are needed after the barrier
-        const int tc = gw / L, tj = gw - tc * L;              // M * L <= nw: one (chain, position) per warp
+        const int tc = gw / L, tj = gw - tc * L;              // one (chain, position) per warp (the whole GPU on one view: M * L <= nw)
         const bool act = tc < M && pos[tc] < len[tc] && cur[tc] == rmin && pos[tc] + tj < len[tc];
         int th = -1, tpa = -1, tpre[NC];
         if (act) th = P.cev[off[tc] + pos[tc] + tj];          // (its dependent loads are issued after the range arithmetic)
@@ -433,6 +433,28 @@ __device__ __forceinline__ void rounds_batch_body(const RbParams &P, const int b
             const long long e1 = clock64() - tS1;
             c_maxev = e1 > c_maxev ? e1 : c_maxev; c_sumev += e1; c_nev++; c_def += hit == 2;
             c_g += tG1 - tG0; c_gmax = max(c_gmax, tG1 - tG0);
+        }
+        // a view that shares the launch with others has fewer warps than (chain, position) pairs: the rest of its tests, in turn
+        for (int item = gw + nw; item < M * L; item += nw) {
+            const int c2 = item / L, j2 = item - c2 * L;
+            if (!(pos[c2] < len[c2] && cur[c2] == rmin && pos[c2] + j2 < len[c2])) continue;
+            const int h2 = P.cev[off[c2] + pos[c2] + j2], pa2 = P.p0[h2];
+            int hit = 0;
+            if (pa2 >= 0) {
+                int pre2[NC], thi[NC];
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const int c = lane + 32 * j;
+                    pre2[j] = c < M ? __ldcg(P.row + (size_t)h2 * M + c) : -1;
+                    if (c == c2) pre2[j] = pa2;
+                    thi[j] = rhi[j];
+                }
+                hit = eval(pre2, thi, rmin, j2 > 0);
+            }
+            if (lane == 0) {
+                if (hit == 1) atomicMin(hitmin + buf * 64 + c2, ((u64)j2 << 32) | (unsigned)h2);
+                if (hit == 2) atomicMin(unkmin + buf * 64 + c2, j2);
+            }
         }
         // the rows the next steps will read first (masks and tests of the events just beyond the windows):
         // pull them into L2 now, off the critical path
