@@ -68,7 +68,8 @@ struct sw_engine {
     // can_see scan scratch (swirld_cansee.cuh)
     int4 *d_cs_meta = nullptr;
     uint8_t *d_cs_wr = nullptr, *d_cs_xb = nullptr, *d_cs_sflag = nullptr;
-    int32_t *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_carry = nullptr, *d_cs_slow = nullptr, *d_cs_slowcnt = nullptr, *d_cs_xlist = nullptr;
+    int32_t *d_cs_last = nullptr, *d_cs_Q = nullptr, *d_cs_carry = nullptr, *d_cs_slow = nullptr, *d_cs_slowcnt = nullptr, *d_cs_xlist = nullptr, *d_cs_slowblk = nullptr, *d_cs_blkcnt = nullptr;
+    std::vector<int32_t> h_stale_cum;    // h_stale_cum[i] = stale other-parents among events [0, i)
     int cs_min_B = 256;           // smallest block length the scan uses (sizes the per-block scratch)
     double *d_t = nullptr;
     uint8_t *d_sig = nullptr;
@@ -248,7 +249,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     C.M = M; C.first = first; C.n = n;
     C.p0 = e->d_p0; C.p1 = e->d_p1; C.creator = e->d_creator; C.stale = e->d_stale; C.row = e->d_row;
     C.meta = e->d_cs_meta; C.wr = e->d_cs_wr; C.xb = e->d_cs_xb; C.last = e->d_cs_last; C.Qtab = e->d_cs_Q;
-    C.carry = e->d_cs_carry; C.slow_list = e->d_cs_slow; C.slow_cnt = e->d_cs_slowcnt; C.sflag = e->d_cs_sflag; C.xlist = e->d_cs_xlist;
+    C.carry = e->d_cs_carry; C.slow_list = e->d_cs_slow; C.slow_cnt = e->d_cs_slowcnt; C.sflag = e->d_cs_sflag; C.xlist = e->d_cs_xlist; C.slow_blk = e->d_cs_slowblk; C.blk_cnt = e->d_cs_blkcnt;
     cudaEvent_t a = get_event(e), b = get_event(e);
     int small_n = 24;
     if (const char *v = getenv("SW_CS_SMALL")) small_n = atoi(v);
@@ -295,19 +296,25 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
         CK(cudaMemsetAsync(e->d_cs_xb + (first & ~3), 0, (size_t)(n + (first & 3)), st));
         CK(cudaMemsetAsync(e->d_cs_sflag + first, 0, (size_t)n, st));
         CK(cudaMemsetAsync(e->d_cs_slowcnt, 0, sizeof(int32_t) * 4, st));
+        CK(cudaMemsetAsync(e->d_cs_blkcnt, 0, sizeof(int32_t) * (size_t)C.nb, st));
     }
+    const bool has_stale = e->h_stale_cum[first + n] - e->h_stale_cum[first] > 0;
     cudaEventRecord(a, st);
     k_cs_prep<<<pblocks, 256, 0, st>>>(C);
-    if (C.nb > 1) k_cs_pass<1><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+    if (C.nb > 1) {
+        if (has_stale) k_cs_pass<1, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+        else k_cs_pass<1, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+    }
     k_cs_heads<<<std::max(1, std::min(2 * e->n_sm, (int)(((size_t)(C.nb + 1) * M + 255) / 256))), 256, 0, st>>>(C);
     if (C.nb > 1) {
         k_cs_check<<<std::max(1, std::min(4 * e->n_sm, (int)(((size_t)C.nb * M + 7) / 8))), 256, 0, st>>>(C);
         const size_t ssm = (size_t)CS_SLOW_WARPS * M * sizeof(int);
         k_cs_slow_wave<<<e->n_sm, CS_SLOW_WARPS * 32, ssm, st>>>(C, 1);
         k_cs_slow_wave<<<e->n_sm, CS_SLOW_WARPS * 32, ssm, st>>>(C, 2);
-        k_cs_slow_rest<<<1, CS_SLOW_WARPS * 32, ssm, st>>>(C, 3);
+        k_cs_slow_rest<<<1, CS_REST_WARPS * 32, (size_t)CS_REST_WARPS * M * sizeof(int), st>>>(C);
     }
-    k_cs_pass<2><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+    if (has_stale) k_cs_pass<2, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+    else k_cs_pass<2, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
     cudaEventRecord(b, st);
     e->spans.push_back(TimedSpan{a, b, 3});
     CK(cudaGetLastError());
@@ -496,6 +503,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
     e->h_head.assign(M, -1);
     e->h_count.assign(M, 0);
     e->h_creator.reserve(e->cap);
+    e->h_stale_cum.assign(1, 0);
     int rc = [&]() -> int {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -512,7 +520,7 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         if (const char *v = getenv("SW_CS_B")) e->cs_min_B = std::max(64, std::min(e->cs_min_B, atoi(v)));
         const size_t nbmax = cap / e->cs_min_B + 3;
         CK(dalloc(&e->d_cs_meta, cap)); CK(dalloc(&e->d_cs_wr, cap)); CK(dalloc(&e->d_cs_xb, cap)); CK(dalloc(&e->d_cs_slow, cap + 4));
-        CK(dalloc(&e->d_cs_last, nbmax * M)); CK(dalloc(&e->d_cs_Q, (nbmax + 1) * M)); CK(dalloc(&e->d_cs_slowcnt, (size_t)4)); CK(dalloc(&e->d_cs_sflag, cap)); CK(dalloc(&e->d_cs_xlist, cap + 4));
+        CK(dalloc(&e->d_cs_last, nbmax * M)); CK(dalloc(&e->d_cs_Q, (nbmax + 1) * M)); CK(dalloc(&e->d_cs_slowcnt, (size_t)4)); CK(dalloc(&e->d_cs_sflag, cap)); CK(dalloc(&e->d_cs_xlist, cap + 4)); CK(dalloc(&e->d_cs_slowblk, cap + 4)); CK(dalloc(&e->d_cs_blkcnt, nbmax + 1));
         CK(dalloc(&e->d_cs_carry, MP));
         CK(dalloc(&e->d_Wf, RM)); CK(dalloc(&e->d_cev, 2 * cap)); /* + the witness list of the current chunk */
         CK(dalloc(&e->d_rbmeta, std::max<size_t>(256, 3 * MP + 64)));
@@ -550,10 +558,12 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(cudaMemcpyAsync(e->d_stake, e->h_stake.data(), sizeof(i64) * M, cudaMemcpyHostToDevice, e->stream));
         // kernels that need more than the default 48 KB of dynamic shared memory
         const size_t cs_smem = (size_t)(M + CS_SV) * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + 3 * CS_TILE;
-        CK(cudaFuncSetAttribute(k_cs_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
-        CK(cudaFuncSetAttribute(k_cs_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         CK(cudaFuncSetAttribute(k_cs_slow_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));
-        CK(cudaFuncSetAttribute(k_cs_slow_rest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));
+        CK(cudaFuncSetAttribute(k_cs_slow_rest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_REST_WARPS * M * sizeof(int))));
         return reset_state(e);
     }();
     if (rc < 0) { g_create_error = e->err; sw_destroy(e); return rc; }
@@ -578,7 +588,7 @@ void sw_destroy(sw_engine *e) {
     if (e->d_stage) cudaFree(e->d_stage);
     for (int p = 0; p < 8; p++) if (e->x_peer[p] && e->x_peer[p] != e->d_xbuf) cudaIpcCloseMemHandle(e->x_peer[p]);
     void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_carry,
-                    e->d_cs_meta, e->d_cs_wr, e->d_cs_xb, e->d_cs_sflag, e->d_cs_xlist, e->d_cs_slow, e->d_cs_slowcnt, e->d_stale, e->d_coin, e->d_dbg, e->d_height,
+                    e->d_cs_meta, e->d_cs_wr, e->d_cs_xb, e->d_cs_sflag, e->d_cs_xlist, e->d_cs_slowblk, e->d_cs_blkcnt, e->d_cs_slow, e->d_cs_slowcnt, e->d_stale, e->d_coin, e->d_dbg, e->d_height,
                     e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_SM,
                     e->d_scw, e->d_sctag, e->d_SMw, e->d_Sw, e->d_hitmin, e->d_xbuf, e->d_xstep,
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_famous, e->d_consensus,
@@ -604,6 +614,7 @@ int sw_reset(sw_engine *e) {
     fold_spans(e);
     e->h_creator.clear();
     e->ids.clear();
+    e->h_stale_cum.assign(1, 0);
     int rc = reset_state(e);
     memset(&e->stats, 0, sizeof e->stats);
     return rc;
@@ -666,6 +677,10 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
         e->h_creator[i] = c;
         e->h_head[c] = i;
         e->h_seq[i] = e->h_count[c]++;
+    }
+    if (rc == SW_OK) {
+        e->h_stale_cum.resize((size_t)base + n + 1);
+        for (int j = 0; j < n; j++) e->h_stale_cum[base + j + 1] = e->h_stale_cum[base + j] + e->h_stale[base + j];
     }
     if (rc != SW_OK) {
         e->h_head = head_save; e->h_count = count_save;
@@ -1272,6 +1287,8 @@ int sw_load(const char *path, int device, int capacity_events, sw_engine **out) 
         && cudaMemcpy(e->d_stale, e->h_stale, (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok2) { sw_destroy(e); return fail(nullptr, SW_E_CUDA, "sw_load: device copy failed"); }
     e->n_events = n; e->n_divided = nd; e->n_tx = H.n_tx; e->n_rowed = nr; e->rb_epoch = H.rb_epoch;
+    e->h_stale_cum.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) e->h_stale_cum[i + 1] = e->h_stale_cum[i] + e->h_stale[i];
     e->stats.events = n; e->stats.events_divided = nd;
     *out = e;
     return SW_OK;

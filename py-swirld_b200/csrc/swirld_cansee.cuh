@@ -43,6 +43,8 @@ struct CsParams {
     int32_t *slow_list;         // [cap] the listed rows that failed the check (any order)
     int32_t *slow_cnt;          // [4]: slow rows, slow rows still pending, rows on xlist; zero on entry
     int32_t *xlist;             // [cap] the rows a later block reads (each once)
+    int32_t *slow_blk;          // [cap] the failed rows again, per block: block j's at [start(j), ..)
+    int32_t *blk_cnt;           // [nb] their counts, zero on entry
     uint8_t *sflag;             // [cap] 0 final, 1 pending slow row, 2 + w finished in wave w of k_cs_slow_*
 };
 
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(256) k_cs_prep(CsParams P) {
 }
 
 // One (block, column tile) per warp.  PASS 1: leaves outside the block, sparse writes.  PASS 2: exact.
-template <int PASS>
+// STALE: the range holds stale other-parents (sw_append counts them); without, the prefetch machinery compiles away
+template <int PASS, bool STALE>
 __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     extern __shared__ int cs_smem[];
     const int CT = P.CT;
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
         // a stale other-parent (not its member's latest event) is read from the table; when it lies before this tile its
         // value is there already: fetch all of the tile's now, eight loads in flight, instead of one memory round trip
         // per event in the walk
-        {
+        if (STALE) {
             int ns = 0;
             for (int i0 = 0; i0 < tn; i0 += CS_CT) {
                 const int i = i0 + tl;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
             const int4 m0 = meta[i];
             const int h = t0 + i;
             bool fast = ((m0.z >> 17) & 1) && i + 4 <= tn;
-            if (fast) {                                    // (a stale member of the group needs its prefetch slot)
+            if (STALE && fast) {                           // (a stale member of the group needs its prefetch slot)
                 const unsigned stm = ((m0.z >> 16) & 1) | (((meta[i + 1].z >> 16) & 1) << 1) | (((meta[i + 2].z >> 16) & 1) << 2) | (((meta[i + 3].z >> 16) & 1) << 3);
                 if (stm) {
 #pragma unroll
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 const int c0 = m0.z & 0xffff, c1 = m1.z & 0xffff, c2 = m2.z & 0xffff, c3 = m3.z & 0xffff;
                 int x0, x1, x2, x3, y0, y1, y2, y3;
                 auto other = [&](const int4 &m, int k) -> int {      // the other-parent's contribution in this column
-                    if ((m.z >> 16) & 1) {
+                    if (STALE && ((m.z >> 16) & 1)) {
                         if (PASS == 1 && m.y < s) return (c == m.w) ? m.y : -1;
                         return svb[sslot[i + k] * CT + lane];
                     }
@@ -227,11 +230,11 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 int x, y;
                 if (PASS == 1) {
                     x = a >= s ? val(cr)[lane] : -1;
-                    if (b >= s) y = st ? (sslot[i] != 255 ? svb[sslot[i] * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane];
+                    if (b >= s) y = (STALE && st) ? (sslot[i] != 255 ? svb[sslot[i] * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane];
                     else y = (b >= 0 && c == cb) ? b : -1;
                 } else {
                     x = val(cr)[lane];
-                    y = b < 0 ? -1 : (st ? (sslot[i] != 255 ? svb[sslot[i] * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane]);
+                    y = b < 0 ? -1 : ((STALE && st) ? (sslot[i] != 255 ? svb[sslot[i] * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane]);
                 }
                 const int v = c == cr ? h : max(x, y);
                 if (own) val(cr)[lane] = v;
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__(256) k_cs_check(CsParams P) {
         if (!__all_sync(0xffffffffu, ok) && lane == 0) {
             P.slow_list[atomicAdd(&P.slow_cnt[0], 1)] = x;
             atomicAdd(&P.slow_cnt[1], 1);
+            P.slow_blk[lim + atomicAdd(&P.blk_cnt[bx], 1)] = x;
             P.sflag[x] = 1;
         }
     }
@@ -365,15 +369,52 @@ __global__ void __launch_bounds__(CS_SLOW_WARPS * 32) k_cs_slow_wave(CsParams P,
     const int warp = threadIdx.x >> 5;
     cs_slow_wave(P, wave, blockIdx.x * CS_SLOW_WARPS + warp, gridDim.x * CS_SLOW_WARPS, cs_smem + (size_t)warp * P.M, threadIdx.x & 31);
 }
-__global__ void __launch_bounds__(CS_SLOW_WARPS * 32) k_cs_slow_rest(CsParams P, int wave0) {
+// What two grid-wide waves left pending (long dependency chains: graphs in which a member's last event of a block often
+// does not see every head, e.g. two cliques with rare cross links): block after block -- a row depends only on rows of
+// EARLIER blocks, so every pending row of block j can be finished once the blocks below are done.  One CTA, the rows of a
+// block across its warps.
+#define CS_REST_WARPS 32
+__global__ void __launch_bounds__(CS_REST_WARPS * 32) k_cs_slow_rest(CsParams P) {
     extern __shared__ int cs_smem[];
     if (P.slow_cnt[1] <= 0) return;
-    const int warp = threadIdx.x >> 5;
-    for (int wave = wave0; wave < 248; wave++) {                 // (rows stamped in wave w count as final from wave w+1 on)
-        cs_slow_wave(P, wave, warp, CS_SLOW_WARPS, cs_smem + (size_t)warp * P.M, threadIdx.x & 31);
-        __threadfence_block();
-        __syncthreads();
-        if (*(volatile int32_t *)&P.slow_cnt[1] <= 0) break;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, M = P.M;
+    int *ent = cs_smem + (size_t)warp * M;
+    for (int blk = 0; blk < P.nb; blk++) {
+        const int cnt = P.blk_cnt[blk];
+        if (cnt == 0) continue;                                  // (uniform)
+        const int lim = cs_start(P, blk);
+        const int32_t *Q = P.Qtab + (size_t)blk * M;
+        for (int i = warp; i < cnt; i += CS_REST_WARPS) {
+            const int x = P.slow_blk[lim + i];
+            if (P.sflag[x] != 1) continue;
+            for (int m = lane; m < M; m += 32) {
+                const int pr = P.row[(size_t)x * M + m], q = Q[m];
+                ent[m] = (pr >= lim || pr == q) ? q : pr;
+            }
+            __syncwarp();
+            for (int c0 = 0; c0 < M; c0 += 32) {
+                const int c = c0 + lane;
+                bool bad = false;
+                if (c < M) { const int pr = P.row[(size_t)x * M + c]; bad = pr < lim && pr != Q[c]; }
+                unsigned todo = __ballot_sync(0xffffffffu, bad);
+                while (todo) {
+                    const int cb = c0 + __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    int acc = -1;
+                    for (int m = lane; m < M; m += 32) {
+                        const int ev = ent[m];
+                        if (ev >= 0) acc = max(acc, __ldcg(P.row + (size_t)ev * M + cb));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+                    if (lane == 0 && acc > P.row[(size_t)x * M + cb]) P.row[(size_t)x * M + cb] = acc;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) P.sflag[x] = 251;
+        }
+        __threadfence();
+        __syncthreads();                                         // block blk is final before the next one reads it
     }
 }
 
