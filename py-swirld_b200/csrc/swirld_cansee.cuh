@@ -310,6 +310,34 @@ __global__ void __launch_bounds__(256) k_cs_check(CsParams P) {
 // 2 + wave; the others wait for the next wave (the pending rows of the lowest block always finish).  Waves 1 and 2 are
 // grid-wide launches, whatever is left (normally nothing) is finished by one CTA.
 #define CS_SLOW_WARPS 16
+#define CS_COLPAR 8             // a row with more open columns than this is finished with one lane per column
+
+// number of open columns of row x (neither in-block nor the head itself)
+__device__ __forceinline__ int cs_open_count(const CsParams &P, int x, int lim, const int32_t *Q, int lane) {
+    int n = 0;
+    for (int c0 = 0; c0 < P.M; c0 += 32) {
+        const int c = c0 + lane;
+        bool bad = false;
+        if (c < P.M) { const int pr = P.row[(size_t)x * P.M + c]; bad = pr < lim && pr != Q[c]; }
+        n += __popc(__ballot_sync(0xffffffffu, bad));
+    }
+    return n;
+}
+// all open columns of row x at once: lane = column, the entry events in turn (their rows are final)
+__device__ __forceinline__ void cs_finish_row_columns(const CsParams &P, int x, int lim, const int32_t *Q, const int *ent, int lane) {
+    const int M = P.M;
+    for (int c = lane; c < M; c += 32) {
+        const int pr = P.row[(size_t)x * M + c];
+        if (!(pr < lim && pr != Q[c])) continue;
+        int acc = pr;
+#pragma unroll 4
+        for (int m = 0; m < M; m++) {
+            const int ev = ent[m];
+            if (ev >= 0) acc = max(acc, __ldcg(P.row + (size_t)ev * M + c));
+        }
+        if (acc != pr) P.row[(size_t)x * M + c] = acc;
+    }
+}
 __device__ __forceinline__ int cs_slow_wave(const CsParams &P, int wave, int w0, int nwarps, int *ent, int lane) {
     const int M = P.M, cnt = P.slow_cnt[0];
     int done = 0;
@@ -324,6 +352,21 @@ __device__ __forceinline__ int cs_slow_wave(const CsParams &P, int wave, int w0,
         }
         __syncwarp();
         bool complete = true;
+        if (cs_open_count(P, x, lim, Q, lane) > CS_COLPAR) {
+            // many open columns: all at once, one lane per column -- when no entry event is itself a row in flux
+            bool flux = false;
+            for (int m = lane; m < M; m += 32) {
+                const int ev = ent[m];
+                if (ev >= P.first) { const int f = P.sflag[ev]; flux |= f == 1 || f == min(2 + wave, 250); }
+            }
+            if (__any_sync(0xffffffffu, flux)) continue;
+            cs_finish_row_columns(P, x, lim, Q, ent, lane);
+            __syncwarp();
+            __threadfence();
+            if (lane == 0) { P.sflag[x] = (uint8_t)min(2 + wave, 250); atomicSub(&P.slow_cnt[1], 1); }
+            done++;
+            continue;
+        }
         for (int c0 = 0; c0 < M; c0 += 32) {
             const int c = c0 + lane;
             bool bad = false;
@@ -392,6 +435,12 @@ __global__ void __launch_bounds__(CS_REST_WARPS * 32) k_cs_slow_rest(CsParams P)
                 ent[m] = (pr >= lim || pr == q) ? q : pr;
             }
             __syncwarp();
+            if (cs_open_count(P, x, lim, Q, lane) > CS_COLPAR) {
+                cs_finish_row_columns(P, x, lim, Q, ent, lane);
+                __syncwarp();
+                if (lane == 0) P.sflag[x] = 251;
+                continue;
+            }
             for (int c0 = 0; c0 < M; c0 += 32) {
                 const int c = c0 + lane;
                 bool bad = false;
