@@ -274,11 +274,13 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     if (C.nb > 1 && first + n - (C.first_al + (C.nb - 1) * B) < 3 * B / 4) C.nb--;     // a short tail joins the block before it
     // columns per tile: 32 (one warp = one 128-byte row segment) unless the per-member cache val[M][CT] then limits a
     // SM to so few CTAs that narrower tiles finish in fewer waves (M = 1024: 128 KB per CTA at CT = 32)
+    const bool has_stale = e->h_stale_cum[first + n] - e->h_stale_cum[first] > 0;
+    C.SV = has_stale ? CS_SV : 0;
     int CT = 32;
     {
         long long best = -1;
         for (int ct = 32; ct >= 8; ct >>= 1) {
-            const long long smem_ct = (long long)(M + CS_SV) * ct * 4 + CS_TILE * 16 + 3 * CS_TILE;
+            const long long smem_ct = (long long)(M + C.SV) * ct * 4 + CS_TILE * 16 + 3 * CS_TILE;
             const long long conc = std::max(1LL, std::min(32LL, (220LL << 10) / smem_ct));
             const long long ctas = (long long)C.nb * ((M + ct - 1) / ct);
             const long long waves = (ctas + e->n_sm * conc - 1) / (e->n_sm * conc);
@@ -288,7 +290,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     if (const char *v = getenv("SW_CS_CT")) { const int x = atoi(v); if (x == 8 || x == 16 || x == 32) CT = x; }
     C.CT = CT;
     const int ntiles = (M + CT - 1) / CT;
-    const size_t smem = (size_t)(M + CS_SV) * CT * sizeof(int) + CS_TILE * sizeof(int4) + 3 * CS_TILE;
+    const size_t smem = (size_t)(M + C.SV) * CT * sizeof(int) + CS_TILE * sizeof(int4) + 3 * CS_TILE;
     const int pblocks = std::max(1, std::min(8 * e->n_sm, (n + 255) / 256));
     k_fill_i32<<<std::max(1, std::min(256, (int)(((size_t)C.nb * M + 255) / 256))), 256, 0, st>>>(e->d_cs_last, -1, (size_t)C.nb * M);
     if (C.nb > 1) {
@@ -298,7 +300,6 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
         CK(cudaMemsetAsync(e->d_cs_slowcnt, 0, sizeof(int32_t) * 4, st));
         CK(cudaMemsetAsync(e->d_cs_blkcnt, 0, sizeof(int32_t) * (size_t)C.nb, st));
     }
-    const bool has_stale = e->h_stale_cum[first + n] - e->h_stale_cum[first] > 0;
     cudaEventRecord(a, st);
     k_cs_prep<<<pblocks, 256, 0, st>>>(C);
     if (C.nb > 1) {

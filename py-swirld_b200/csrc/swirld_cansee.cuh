@@ -31,7 +31,8 @@
 
 struct CsParams {
     int M, first, n, B, nb, first_al;   // events [first, first+n); block 0 = [first, first_al+B), block j = [first_al+jB, ..)
-    int CT;                     // columns per tile: 32, or 16 / 8 when there are too few (block, tile) pairs to fill the GPU
+    int CT;                     // columns per tile: 32, or 16 / 8 when the per-member cache would leave a SM too few CTAs
+    int SV;                     // prefetch slots in shared memory: CS_SV when the range holds stale other-parents, else 0
     const int32_t *p0, *p1, *creator;
     const uint8_t *stale;       // [cap] from sw_append: the other-parent is not its member's latest event
     int32_t *row;               // [cap][M]; rows < first are final
@@ -49,7 +50,7 @@ struct CsParams {
 };
 
 #define CS_TILE 128
-#define CS_SV 32                // prefetch slots for the stale other-parents of a tile (the rest is read in the walk)
+#define CS_SV 64                // prefetch slots for the stale other-parents of a tile (the rest is read in the walk)
 #define CS_CT 32                // threads per CTA (one warp); columns per tile = P.CT <= 32
 
 // (the last block takes whatever is left: a short tail block would fail the finality check often, so the host
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     uint8_t *slist = wrt + CS_TILE;                                                // [CS_SV] tile positions of the prefetched stale parents
     uint8_t *sslot = slist + CS_TILE;                                              // [CS_TILE] tile position -> prefetch slot, 255 none
     int *svb = cs_smem + CS_TILE * 4 + 3 * CS_TILE / 4;                            // [CS_SV][CT] prefetched rows of stale other-parents
-    int *valb = svb + CS_SV * CT;                                                  // [M][CT]
+    int *valb = svb + P.SV * CT;                                                   // [M][CT]
     const int tl = threadIdx.x, M = P.M, blk = blockIdx.x;
     const int lane = tl & (CT - 1);                                                // lanes >= CT shadow lane % CT (their stores are off)
     const int c = blockIdx.y * CT + lane;
@@ -165,17 +166,17 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
             }
             ns = min(ns, CS_SV);
             __syncwarp();
-            for (int k0 = 0; k0 < ns; k0 += 8) {
-                int v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = slist[min(k0 + u, ns - 1)];
-                    v[u] = col ? rowc[(size_t)meta[i].y * M] : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (k0 + u < ns && own) svb[(k0 + u) * CT + lane] = v[u];
+            // every lane copies its own column of every prefetched row straight into shared memory: all in flight at once
+            for (int k = 0; k < ns; k++) {
+                if (!own) break;
+                int *dst = svb + k * CT + lane;
+                if (col) {
+                    const int32_t *src = rowc + (size_t)meta[slist[k]].y * M;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+                } else *dst = -1;
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
         }
         int i = 0;
         while (i < tn) {
