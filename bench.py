@@ -196,7 +196,7 @@ def python_reference_sample(tr, wl):
     try:
         import ref_harness as rh
         M = wl["M"]
-        n = min(tr.N, max(2000 if M <= 256 else 600, int(12 * 5.6e3 * (64.0 / max(M, 8)) ** 2)))     # ~10-30 s of CPython
+        n = min(tr.N, max(2000, 3 * M, int(12 * 5.6e3 * (64.0 / max(M, 8)) ** 2)))     # ~10-40 s of CPython; past the M root events
         K = min(wl["K"], 2000) if n > 2000 else wl["K"]
         r = rh.run_reference(tr.slice(0, n), K)
         s = r["t_divide_rounds"] + r["t_decide_fame"]
