@@ -116,8 +116,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     const int CT = P.CT;
     int4 *meta = reinterpret_cast<int4 *>(cs_smem);                                // [CS_TILE]
     uint8_t *wrt = reinterpret_cast<uint8_t *>(meta + CS_TILE);                    // [CS_TILE]
-    uint8_t *slist = wrt + CS_TILE;                                                // [CS_SV] tile positions of the prefetched stale parents
-    uint8_t *sslot = slist + CS_TILE;                                              // [CS_TILE] tile position -> prefetch slot, 255 none
+    uint8_t *slist = wrt + CS_TILE;                                                // 2 * CS_TILE bytes: the prefetched parents' indices
     int *svb = cs_smem + CS_TILE * 4 + 3 * CS_TILE / 4;                            // [CS_SV][CT] prefetched rows of stale other-parents
     int *valb = svb + P.SV * CT;                                                   // [M][CT]
     const int tl = threadIdx.x, M = P.M, blk = blockIdx.x;
@@ -153,27 +152,32 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
         // value is there already: fetch all of the tile's now, eight loads in flight, instead of one memory round trip
         // per event in the walk
         if (STALE) {
+            // prefetch slot k <- the stale other-parent of tile position i: its index goes to sb[k] and the tile's copy of
+            // the event is re-coded (p1 := -(k + 2)) so that the walk finds the slot without another lookup
+            int *sb = reinterpret_cast<int *>(slist);           // [CS_SV] (the two byte arrays' space: 2 * CS_TILE bytes)
             int ns = 0;
             for (int i0 = 0; i0 < tn; i0 += CS_CT) {
                 const int i = i0 + tl;
                 bool pf = false;
-                if (i < tn) { const int4 mi = meta[i]; pf = ((mi.z >> 16) & 1) && mi.y < t0 && (PASS == 2 || mi.y >= s); }
+                int b = -1;
+                if (i < tn) { const int4 mi = meta[i]; b = mi.y; pf = ((mi.z >> 16) & 1) && b < t0 && (PASS == 2 || b >= s); }
                 const unsigned bal = __ballot_sync(0xffffffffu, pf);
                 const int slot = ns + __popc(bal & ((1u << tl) - 1));
-                if (i < tn) sslot[i] = (pf && slot < CS_SV) ? (uint8_t)slot : (uint8_t)255;
-                if (pf && slot < CS_SV) slist[slot] = (uint8_t)i;
+                if (pf && slot < CS_SV) { sb[slot] = b; meta[i].y = -(slot + 2); }
                 ns += __popc(bal);
             }
             ns = min(ns, CS_SV);
             __syncwarp();
             // every lane copies its own column of every prefetched row straight into shared memory: all in flight at once
-            for (int k = 0; k < ns; k++) {
-                if (!own) break;
-                int *dst = svb + k * CT + lane;
-                if (col) {
-                    const int32_t *src = rowc + (size_t)meta[slist[k]].y * M;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-                } else *dst = -1;
+            if (own) {
+#pragma unroll 4
+                for (int k = 0; k < ns; k++) {
+                    int *dst = svb + k * CT + lane;
+                    if (col) {
+                        const int32_t *src = rowc + (size_t)sb[k] * M;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+                    } else *dst = -1;
+                }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 if (stm) {
 #pragma unroll
                     for (int u = 0; u < 4; u++)
-                        if (((stm >> u) & 1) && !(PASS == 1 && meta[i + u].y < s) && sslot[i + u] == 255) fast = false;
+                        if (((stm >> u) & 1) && meta[i + u].y > -2 && !(PASS == 1 && meta[i + u].y < s)) fast = false;
                 }
             }
             if (fast) {
@@ -198,8 +202,8 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 int x0, x1, x2, x3, y0, y1, y2, y3;
                 auto other = [&](const int4 &m, int k) -> int {      // the other-parent's contribution in this column
                     if (STALE && ((m.z >> 16) & 1)) {
-                        if (PASS == 1 && m.y < s) return (c == m.w) ? m.y : -1;
-                        return svb[sslot[i + k] * CT + lane];
+                        if (m.y <= -2) return svb[(-m.y - 2) * CT + lane];
+                        return (c == m.w) ? m.y : -1;                // (pass 1, a stale parent below the block: a leaf)
                     }
                     if (PASS == 1) return m.y >= s ? val(m.w)[lane] : ((m.y >= 0 && c == m.w) ? m.y : -1);
                     return m.y >= 0 ? val(m.w)[lane] : -1;
@@ -231,11 +235,13 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 int x, y;
                 if (PASS == 1) {
                     x = a >= s ? val(cr)[lane] : -1;
-                    if (b >= s) y = (STALE && st) ? (sslot[i] != 255 ? svb[sslot[i] * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane];
+                    if (STALE && st && b <= -2) y = svb[(-b - 2) * CT + lane];
+                    else if (b >= s) y = (STALE && st) ? (col ? rowc[(size_t)b * M] : -1) : val(cb)[lane];
                     else y = (b >= 0 && c == cb) ? b : -1;
                 } else {
                     x = val(cr)[lane];
-                    y = b < 0 ? -1 : ((STALE && st) ? (sslot[i] != 255 ? svb[sslot[i] * CT + lane] : (col ? rowc[(size_t)b * M] : -1)) : val(cb)[lane]);
+                    if (STALE && st && b <= -2) y = svb[(-b - 2) * CT + lane];
+                    else y = b < 0 ? -1 : ((STALE && st) ? (col ? rowc[(size_t)b * M] : -1) : val(cb)[lane]);
                 }
                 const int v = c == cr ? h : max(x, y);
                 if (own) val(cr)[lane] = v;
