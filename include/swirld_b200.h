@@ -149,15 +149,18 @@ int sw_lookup(sw_engine *e, int n, const uint8_t *ids, int32_t *index_out);   /*
 int sw_save(sw_engine *e, const char *path);
 int sw_load(const char *path, int device, int capacity_events, sw_engine **out);
 
-/* ---- several GPUs of one box (one process per GPU), M > 64: ONE hashgraph, the P_r tests of every round step of
- * sw_divide_rounds sharded by member chain over the ranks; every rank writes its chains' first hits straight into
- * every peer's exchange buffer over NVLink (P2P stores + a system-scope flag) from inside the round kernel -- no
- * collective library call on the data path, identical state and results on every rank.  (The reference has no
- * counterpart: it is single-process, swirld.py:331-345.)  sw_peer_handle: the 64-byte CUDA IPC handle of this
- * engine's exchange buffer; exchange the handles out of band (torch.distributed.all_gather_object), then
- * sw_peer_connect(rank, nranks <= 8, handles[nranks][64]) before the first sw_divide_rounds.  Every rank must then
- * make the same sw_append / sw_divide_rounds calls. */
-int sw_peer_handle(sw_engine *e, void *handle_out64);
+/* ---- several GPUs of one box (one process per GPU), M > 64: ONE hashgraph, identical state and results on every rank,
+ * no collective library call on the data path (the reference has no counterpart: it is single-process, swirld.py:331-345):
+ *  - can_see: the column tiles of the scan are split over the ranks and every walk stores its row segments straight into
+ *    EVERY rank's table over NVLink (P2P stores: the all-gather of the table is fused into the kernel that produces it);
+ *  - divide_rounds: the P_r tests of every round step are sharded by member chain; every rank writes its chains' first
+ *    hits into every peer's exchange buffer (P2P stores + a system-scope flag) from inside the round kernel.
+ * sw_peer_handle writes SW_PEER_HANDLE_BYTES bytes (the CUDA IPC handles of this engine's exchange buffer and can_see
+ * table); exchange them out of band (torch.distributed.all_gather_object), then
+ * sw_peer_connect(rank, nranks <= 8, handles[nranks][SW_PEER_HANDLE_BYTES]) before the first sw_append.  Every rank must
+ * then make the same sw_append / sw_divide_rounds / ... calls. */
+#define SW_PEER_HANDLE_BYTES 128
+int sw_peer_handle(sw_engine *e, void *handle_out);
 int sw_peer_connect(sw_engine *e, int rank, int nranks, const void *handles);
 
 int sw_version(void);

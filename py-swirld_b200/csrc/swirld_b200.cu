@@ -84,6 +84,9 @@ struct sw_engine {
     int rank = 0, nranks = 1;
     void *d_xbuf = nullptr;       // [flags: 64 x u32][hits: 8 x 3 x M x u64], IPC-exported
     void *x_peer[8] = {nullptr};  // the same buffer of every rank (own: d_xbuf)
+    int32_t *row_peer[8] = {nullptr};   // every rank's can_see table (own: d_row)
+    unsigned **d_xflags2 = nullptr;     // device array of the ranks' barrier flag rows (xbuf + 128 bytes)
+    unsigned xbar_count = 0;      // cross-GPU barriers issued so far (identical on every rank)
     unsigned *d_xstep = nullptr;  // steps published so far (device-resident: the step count of a launch is data dependent)
     // per round
     int32_t *d_W = nullptr, *d_rem = nullptr, *d_newc = nullptr;
@@ -289,7 +292,21 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     }
     if (const char *v = getenv("SW_CS_CT")) { const int x = atoi(v); if (x == 8 || x == 16 || x == 32) CT = x; }
     C.CT = CT;
-    const int ntiles = (M + CT - 1) / CT;
+    int tile_lo = 0, tile_hi = (M + CT - 1) / CT;
+    if (e->nranks > 1) {                                  // the column tiles of this rank; every rank stores into every table
+        const int nt = tile_hi;
+        tile_lo = (int)((long long)nt * e->rank / e->nranks); tile_hi = (int)((long long)nt * (e->rank + 1) / e->nranks);
+        C.npeer = e->nranks;
+        for (int p = 0; p < e->nranks; p++) C.prow[p] = e->row_peer[p];
+    }
+    C.tile_lo = tile_lo;
+    const int ntiles = std::max(0, tile_hi - tile_lo);
+    auto xbarrier = [&]() -> int {
+        if (e->nranks <= 1) return 0;
+        k_xbarrier<<<1, 32, 0, st>>>(e->d_xflags2, e->rank, e->nranks, ++e->xbar_count, e->d_scal);
+        CK(cudaGetLastError());
+        return 0;
+    };
     const size_t smem = (size_t)(M + C.SV) * CT * sizeof(int) + CS_TILE * sizeof(int4) + 3 * CS_TILE;
     const int pblocks = std::max(1, std::min(8 * e->n_sm, (n + 255) / 256));
     k_fill_i32<<<std::max(1, std::min(256, (int)(((size_t)C.nb * M + 255) / 256))), 256, 0, st>>>(e->d_cs_last, -1, (size_t)C.nb * M);
@@ -303,8 +320,11 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     cudaEventRecord(a, st);
     k_cs_prep<<<pblocks, 256, 0, st>>>(C);
     if (C.nb > 1) {
-        if (has_stale) k_cs_pass<1, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
-        else k_cs_pass<1, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+        if (ntiles > 0) {
+            if (has_stale) k_cs_pass<1, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+            else k_cs_pass<1, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+        }
+        if (xbarrier() < 0) return SW_E_CUDA;              // every rank's partial rows are in every table
     }
     k_cs_heads<<<std::max(1, std::min(2 * e->n_sm, (int)(((size_t)(C.nb + 1) * M + 255) / 256))), 256, 0, st>>>(C);
     if (C.nb > 1) {
@@ -314,8 +334,12 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
         k_cs_slow_wave<<<e->n_sm, CS_SLOW_WARPS * 32, ssm, st>>>(C, 2);
         k_cs_slow_rest<<<1, CS_REST_WARPS * 32, (size_t)CS_REST_WARPS * M * sizeof(int), st>>>(C);
     }
-    if (has_stale) k_cs_pass<2, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
-    else k_cs_pass<2, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+    if (ntiles > 0) {
+        if (has_stale) k_cs_pass<2, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+        else k_cs_pass<2, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+    }
+    if (e->nranks > 1) k_cs_carry<<<(M + 255) / 256, 256, 0, st>>>(C);
+    if (xbarrier() < 0) return SW_E_CUDA;                  // the whole table is in every rank's memory
     cudaEventRecord(b, st);
     e->spans.push_back(TimedSpan{a, b, 3});
     CK(cudaGetLastError());
@@ -588,6 +612,8 @@ void sw_destroy(sw_engine *e) {
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->d_stage) cudaFree(e->d_stage);
     for (int p = 0; p < 8; p++) if (e->x_peer[p] && e->x_peer[p] != e->d_xbuf) cudaIpcCloseMemHandle(e->x_peer[p]);
+    for (int p = 0; p < 8; p++) if (e->row_peer[p] && e->row_peer[p] != e->d_row) cudaIpcCloseMemHandle(e->row_peer[p]);
+    if (e->d_xflags2) cudaFree(e->d_xflags2);
     void *ptrs[] = {e->d_rbtot, e->d_gchain, e->d_Wf, e->d_cev, e->d_rbmeta, e->d_sc, e->d_res, e->d_cs_last, e->d_cs_Q, e->d_cs_carry,
                     e->d_cs_meta, e->d_cs_wr, e->d_cs_xb, e->d_cs_sflag, e->d_cs_xlist, e->d_cs_slowblk, e->d_cs_blkcnt, e->d_cs_slow, e->d_cs_slowcnt, e->d_stale, e->d_coin, e->d_dbg, e->d_height,
                     e->d_p0, e->d_p1, e->d_creator, e->d_seq, e->d_t, e->d_sig, e->d_row, e->d_SM,
@@ -1304,6 +1330,8 @@ int sw_peer_handle(sw_engine *e, void *handle_out64) {
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, e->d_xbuf));
     memcpy(handle_out64, &h, 64);
+    CK(cudaIpcGetMemHandle(&h, e->d_row));
+    memcpy(reinterpret_cast<char *>(handle_out64) + 64, &h, 64);
     return SW_OK;
 }
 
@@ -1313,13 +1341,22 @@ int sw_peer_connect(sw_engine *e, int rank, int nranks, const void *handles) {
     if (e->n_divided > 0) return fail(e, SW_E_ARG, "sw_peer_connect: connect before the first divide_rounds");
     CK(cudaSetDevice(e->device));
     for (int p = 0; p < nranks; p++) {
-        if (p == rank) { e->x_peer[p] = e->d_xbuf; continue; }
+        if (p == rank) { e->x_peer[p] = e->d_xbuf; e->row_peer[p] = e->d_row; continue; }
         cudaIpcMemHandle_t h;
-        memcpy(&h, reinterpret_cast<const char *>(handles) + (size_t)64 * p, 64);
+        memcpy(&h, reinterpret_cast<const char *>(handles) + (size_t)SW_PEER_HANDLE_BYTES * p, 64);
         void *ptr = nullptr;
         CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         e->x_peer[p] = ptr;
+        memcpy(&h, reinterpret_cast<const char *>(handles) + (size_t)SW_PEER_HANDLE_BYTES * p + 64, 64);
+        ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        e->row_peer[p] = reinterpret_cast<int32_t *>(ptr);
     }
+    // the ranks' barrier flag rows (128 bytes into the exchange buffer) as a device array
+    unsigned *fl[8] = {nullptr};
+    for (int p = 0; p < nranks; p++) fl[p] = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(e->x_peer[p]) + 128);
+    if (!e->d_xflags2) CK(cudaMalloc((void **)&e->d_xflags2, sizeof(unsigned *) * 8));
+    CK(cudaMemcpy(e->d_xflags2, fl, sizeof fl, cudaMemcpyHostToDevice));
     e->rank = rank; e->nranks = nranks;
     return SW_OK;
 }

@@ -33,6 +33,10 @@ struct CsParams {
     int M, first, n, B, nb, first_al;   // events [first, first+n); block 0 = [first, first_al+B), block j = [first_al+jB, ..)
     int CT;                     // columns per tile: 32, or 16 / 8 when the per-member cache would leave a SM too few CTAs
     int SV;                     // prefetch slots in shared memory: CS_SV when the range holds stale other-parents, else 0
+    // several GPUs (sw_peer_connect): the column tiles are split over the ranks and every row segment a walk produces
+    // is stored straight into EVERY rank's table over NVLink (the all-gather of the can_see table, fused into the walk)
+    int tile_lo, npeer;         // first tile of this rank; 0 = single GPU
+    int32_t *prow[8];           // peer p's table (own: row)
     const int32_t *p0, *p1, *creator;
     const uint8_t *stale;       // [cap] from sw_append: the other-parent is not its member's latest event
     int32_t *row;               // [cap][M]; rows < first are final
@@ -108,6 +112,12 @@ __global__ void __launch_bounds__(256) k_cs_prep(CsParams P) {
     }
 }
 
+// a row segment goes to this rank's table, or to every rank's (P2P stores over NVLink)
+__device__ __forceinline__ void cs_store(const CsParams &P, size_t idx, int v) {
+    if (P.npeer == 0) { P.row[idx] = v; return; }
+    for (int p = 0; p < P.npeer; p++) P.prow[p][idx] = v;
+}
+
 // One (block, column tile) per warp.  PASS 1: leaves outside the block, sparse writes.  PASS 2: exact.
 // STALE: the range holds stale other-parents (sw_append counts them); without, the prefetch machinery compiles away
 template <int PASS, bool STALE>
@@ -121,14 +131,15 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     int *valb = svb + P.SV * CT;                                                   // [M][CT]
     const int tl = threadIdx.x, M = P.M, blk = blockIdx.x;
     const int lane = tl & (CT - 1);                                                // lanes >= CT shadow lane % CT (their stores are off)
-    const int c = blockIdx.y * CT + lane;
+    const int c = (blockIdx.y + P.tile_lo) * CT + lane;
     const bool own = tl < CT;                                                      // (a shadow lane never stores)
     const bool col = own && c < M;
-    if (PASS == 2 && blockIdx.x == 0 && blockIdx.y == 0)                           // the next launch's carry heads
+    if (PASS == 2 && blockIdx.x == 0 && blockIdx.y == 0 && P.npeer == 0)           // the next launch's carry heads (several ranks: k_cs_carry)
         for (int m = tl; m < M; m += CS_CT) P.carry[m] = P.Qtab[(size_t)P.nb * M + m];
 #define val(m) (valb + (size_t)(m) * CT)
     const int s = cs_start(P, blk), e = cs_end(P, blk);
     int32_t *rowc = P.row + (col ? c : 0);
+    const size_t cc = col ? c : 0;                                                 // (stores: cs_store(P, h * M + cc, v))
     if (PASS == 1) {
         for (int m = 0; m < M; m++) if (own) val(m)[lane] = -1;
     } else {
@@ -220,14 +231,14 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 if (own) { val(c0)[lane] = v0; val(c1)[lane] = v1; val(c2)[lane] = v2; val(c3)[lane] = v3; }
                 if (PASS == 2) {
                     if (col) {
-                        rowc[(size_t)h * M] = v0; rowc[(size_t)(h + 1) * M] = v1;
-                        rowc[(size_t)(h + 2) * M] = v2; rowc[(size_t)(h + 3) * M] = v3;
+                        cs_store(P, (size_t)h * M + cc, v0); cs_store(P, (size_t)(h + 1) * M + cc, v1);
+                        cs_store(P, (size_t)(h + 2) * M + cc, v2); cs_store(P, (size_t)(h + 3) * M + cc, v3);
                     }
                 } else if (col) {
-                    if (wrt[i]) rowc[(size_t)h * M] = v0;
-                    if (wrt[i + 1]) rowc[(size_t)(h + 1) * M] = v1;
-                    if (wrt[i + 2]) rowc[(size_t)(h + 2) * M] = v2;
-                    if (wrt[i + 3]) rowc[(size_t)(h + 3) * M] = v3;
+                    if (wrt[i]) cs_store(P, (size_t)h * M + cc, v0);
+                    if (wrt[i + 1]) cs_store(P, (size_t)(h + 1) * M + cc, v1);
+                    if (wrt[i + 2]) cs_store(P, (size_t)(h + 2) * M + cc, v2);
+                    if (wrt[i + 3]) cs_store(P, (size_t)(h + 3) * M + cc, v3);
                 }
                 i += 4;
             } else {
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 }
                 const int v = c == cr ? h : max(x, y);
                 if (own) val(cr)[lane] = v;
-                if (col && (PASS == 2 || wrt[i])) rowc[(size_t)h * M] = v;
+                if (col && (PASS == 2 || wrt[i])) cs_store(P, (size_t)h * M + cc, v);
                 i += 1;
             }
         }
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
 #pragma unroll
             for (int u = 0; u < 8; u++) l[u] = m0 + u < M ? __ldg(L + m0 + u) : -1;
 #pragma unroll
-            for (int u = 0; u < 8; u++) if (l[u] >= 0) rowc[(size_t)l[u] * M] = val(m0 + u)[lane];
+            for (int u = 0; u < 8; u++) if (l[u] >= 0) cs_store(P, (size_t)l[u] * M + cc, val(m0 + u)[lane]);
         }
     }
 #undef val
@@ -485,4 +496,28 @@ __global__ void __launch_bounds__(1024) k_cs_small(CsParams P) {
         }
         if (threadIdx.x == 0) P.carry[cr] = h;
     }
+}
+
+// Cross-GPU barrier between two kernels of the scan (several ranks): one warp; rank r stores `count` into slot r of every
+// peer's flag row (after a system-scope fence: everything this rank stored into the peers' tables before is visible first),
+// then waits until its own row shows `count` from every rank.  Bounded: ~4 s, then the engine's error flag.
+__global__ void k_xbarrier(unsigned *const *peer_flags, int rank, int nranks, unsigned count, int32_t *scal) {
+    const int t = threadIdx.x;
+    __threadfence_system();
+    if (t < nranks) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(peer_flags[t] + rank), "r"(count) : "memory");
+    if (t < nranks) {
+        const long long t0 = clock64();
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(peer_flags[rank] + t) : "memory");
+            if ((int)(v - count) >= 0) break;
+            if (clock64() - t0 > 8000000000ll) { atomicMin(&scal[SC_ERR], -4); break; }
+        }
+    }
+    __threadfence_system();
+}
+
+// several ranks: a rank may own no column tile at all, so the carry heads are installed by their own little kernel
+__global__ void k_cs_carry(CsParams P) {
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < P.M; m += gridDim.x * blockDim.x) P.carry[m] = P.Qtab[(size_t)P.nb * P.M + m];
 }

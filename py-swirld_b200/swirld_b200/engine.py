@@ -13,6 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswirld_b200.so")
+PEER_HANDLE_BYTES = 128          # SW_PEER_HANDLE_BYTES
 
 SW_E = {-1: "SW_E_ARG", -2: "SW_E_INDEX", -3: "SW_E_KEY", -4: "SW_E_CUDA", -5: "SW_E_CAPACITY",
         -6: "SW_E_PARENT", -7: "SW_E_FORK", -8: "SW_E_UNSUPPORTED"}
@@ -289,14 +290,14 @@ class Engine:
 
     # -- several GPUs of one box, M > 64 (include/swirld_b200.h: sw_peer_handle / sw_peer_connect)
     def peer_handle(self) -> bytes:
-        """The 64-byte CUDA IPC handle of this engine's exchange buffer."""
-        buf = C.create_string_buffer(64)
+        """The CUDA IPC handles (PEER_HANDLE_BYTES bytes) of this engine's exchange buffer and can_see table."""
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
         self._chk(self._lib.sw_peer_handle(self._h, C.cast(buf, C.c_void_p)))
         return buf.raw
 
     def peer_connect(self, rank: int, nranks: int, handles: bytes):
         """handles = the nranks handles concatenated in rank order; call before the first divide_rounds."""
-        assert len(handles) == 64 * nranks
+        assert len(handles) == PEER_HANDLE_BYTES * nranks
         buf = C.create_string_buffer(handles, len(handles))
         self._chk(self._lib.sw_peer_connect(self._h, rank, nranks, C.cast(buf, C.c_void_p)))
 
