@@ -293,7 +293,9 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     if (const char *v = getenv("SW_CS_CT")) { const int x = atoi(v); if (x == 8 || x == 16 || x == 32) CT = x; }
     C.CT = CT;
     int tile_lo = 0, tile_hi = (M + CT - 1) / CT;
-    if (e->nranks > 1) {                                  // the column tiles of this rank; every rank stores into every table
+    bool shard = e->nranks > 1;
+    if (const char *v = getenv("SW_CS_SHARD")) shard = shard && atoi(v) != 0;       // (0: every rank computes the whole table itself)
+    if (shard) {                                          // the column tiles of this rank; every rank stores into every table
         const int nt = tile_hi;
         tile_lo = (int)((long long)nt * e->rank / e->nranks); tile_hi = (int)((long long)nt * (e->rank + 1) / e->nranks);
         C.npeer = e->nranks;
@@ -302,7 +304,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     C.tile_lo = tile_lo;
     const int ntiles = std::max(0, tile_hi - tile_lo);
     auto xbarrier = [&]() -> int {
-        if (e->nranks <= 1) return 0;
+        if (!shard) return 0;
         k_xbarrier<<<1, 32, 0, st>>>(e->d_xflags2, e->rank, e->nranks, ++e->xbar_count, e->d_scal);
         CK(cudaGetLastError());
         return 0;
@@ -338,7 +340,7 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
         if (has_stale) k_cs_pass<2, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
         else k_cs_pass<2, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
     }
-    if (e->nranks > 1) k_cs_carry<<<(M + 255) / 256, 256, 0, st>>>(C);
+    if (shard) k_cs_carry<<<(M + 255) / 256, 256, 0, st>>>(C);
     if (xbarrier() < 0) return SW_E_CUDA;                  // the whole table is in every rank's memory
     cudaEventRecord(b, st);
     e->spans.push_back(TimedSpan{a, b, 3});
@@ -748,7 +750,9 @@ int sw_append(sw_engine *e, int n, const int32_t *p0, const int32_t *p1, const i
         CK(cudaMemcpyAsync(e->d_stale + base, e->h_stale + base, (size_t)n, cudaMemcpyHostToDevice, cs));
     }
     // rows are up to date and the batch is big: scan it now, beside the kernels of the previous chunk
-    const bool eager = e->n_rowed == base && n >= 4096;
+    // (several ranks: the scan holds cross-GPU barriers; it must not run beside a round kernel that fills every SM while
+    //  waiting for the same peer -- scans stay on the compute stream then)
+    const bool eager = e->n_rowed == base && n >= 4096 && e->nranks == 1;
     e->stats.h2d_bytes += (i64)n * (5 * 4 + 1 + 8 + 64);
     e->stats.events += n;
     e->n_events += n;
