@@ -563,7 +563,7 @@ def bench_ours(args, wl, rank, world, local_rank):
                    "famous": bool(np.array_equal(ores["famous"], got_fam))}
             cpu_sample = "full trace (%d events)" % n_cpu
         else:
-            npre = max(2000, min(N, int(30 * port_rate_guess(M))))
+            npre = max(2000, 3 * M, min(N, int((30 if world == 1 else 10) * port_rate_guess(M))))   # (the other ranks wait: keep it short)
             n_cpu, s_cpu, fo_cpu, ores = run_cpu_pass(tr, npre, limit=npre)
             e2 = engine.Engine(M, npre, device=local_rank)
             e2.append_trace(tr, 0, npre)
