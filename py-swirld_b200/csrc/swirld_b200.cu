@@ -323,8 +323,9 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
     k_cs_prep<<<pblocks, 256, 0, st>>>(C);
     if (C.nb > 1) {
         if (ntiles > 0) {
-            if (has_stale) k_cs_pass<1, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
-            else k_cs_pass<1, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+            const dim3 g(C.nb, ntiles);
+            if (shard) { if (has_stale) k_cs_pass<1, true, true><<<g, CS_CT, smem, st>>>(C); else k_cs_pass<1, false, true><<<g, CS_CT, smem, st>>>(C); }
+            else { if (has_stale) k_cs_pass<1, true, false><<<g, CS_CT, smem, st>>>(C); else k_cs_pass<1, false, false><<<g, CS_CT, smem, st>>>(C); }
         }
         if (xbarrier() < 0) return SW_E_CUDA;              // every rank's partial rows are in every table
     }
@@ -337,8 +338,9 @@ int cansee_scan(sw_engine *e, cudaStream_t st, int upto) {
         k_cs_slow_rest<<<1, CS_REST_WARPS * 32, (size_t)CS_REST_WARPS * M * sizeof(int), st>>>(C);
     }
     if (ntiles > 0) {
-        if (has_stale) k_cs_pass<2, true><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
-        else k_cs_pass<2, false><<<dim3(C.nb, ntiles), CS_CT, smem, st>>>(C);
+        const dim3 g(C.nb, ntiles);
+        if (shard) { if (has_stale) k_cs_pass<2, true, true><<<g, CS_CT, smem, st>>>(C); else k_cs_pass<2, false, true><<<g, CS_CT, smem, st>>>(C); }
+        else { if (has_stale) k_cs_pass<2, true, false><<<g, CS_CT, smem, st>>>(C); else k_cs_pass<2, false, false><<<g, CS_CT, smem, st>>>(C); }
     }
     if (shard) k_cs_carry<<<(M + 255) / 256, 256, 0, st>>>(C);
     if (xbarrier() < 0) return SW_E_CUDA;                  // the whole table is in every rank's memory
@@ -585,10 +587,14 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         CK(cudaMemcpyAsync(e->d_stake, e->h_stake.data(), sizeof(i64) * M, cudaMemcpyHostToDevice, e->stream));
         // kernels that need more than the default 48 KB of dynamic shared memory
         const size_t cs_smem = (size_t)(M + CS_SV) * CS_CT * sizeof(int) + CS_TILE * sizeof(int4) + 3 * CS_TILE;
-        CK(cudaFuncSetAttribute(k_cs_pass<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
-        CK(cudaFuncSetAttribute(k_cs_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
-        CK(cudaFuncSetAttribute(k_cs_pass<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
-        CK(cudaFuncSetAttribute(k_cs_pass<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+        CK(cudaFuncSetAttribute(k_cs_pass<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
         CK(cudaFuncSetAttribute(k_cs_slow_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_SLOW_WARPS * M * sizeof(int))));
         CK(cudaFuncSetAttribute(k_cs_slow_rest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CS_REST_WARPS * M * sizeof(int))));
         return reset_state(e);

@@ -113,14 +113,15 @@ __global__ void __launch_bounds__(256) k_cs_prep(CsParams P) {
 }
 
 // a row segment goes to this rank's table, or to every rank's (P2P stores over NVLink)
+template <bool MULTI>
 __device__ __forceinline__ void cs_store(const CsParams &P, size_t idx, int v) {
-    if (P.npeer == 0) { P.row[idx] = v; return; }
-    for (int p = 0; p < P.npeer; p++) P.prow[p][idx] = v;
+    if (MULTI) { for (int p = 0; p < P.npeer; p++) P.prow[p][idx] = v; }
+    else P.row[idx] = v;
 }
 
 // One (block, column tile) per warp.  PASS 1: leaves outside the block, sparse writes.  PASS 2: exact.
 // STALE: the range holds stale other-parents (sw_append counts them); without, the prefetch machinery compiles away
-template <int PASS, bool STALE>
+template <int PASS, bool STALE, bool MULTI>
 __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     extern __shared__ int cs_smem[];
     const int CT = P.CT;
@@ -131,15 +132,15 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
     int *valb = svb + P.SV * CT;                                                   // [M][CT]
     const int tl = threadIdx.x, M = P.M, blk = blockIdx.x;
     const int lane = tl & (CT - 1);                                                // lanes >= CT shadow lane % CT (their stores are off)
-    const int c = (blockIdx.y + P.tile_lo) * CT + lane;
+    const int c = (blockIdx.y + (MULTI ? P.tile_lo : 0)) * CT + lane;
     const bool own = tl < CT;                                                      // (a shadow lane never stores)
     const bool col = own && c < M;
-    if (PASS == 2 && blockIdx.x == 0 && blockIdx.y == 0 && P.npeer == 0)           // the next launch's carry heads (several ranks: k_cs_carry)
+    if (PASS == 2 && blockIdx.x == 0 && blockIdx.y == 0 && !MULTI)           // the next launch's carry heads (several ranks: k_cs_carry)
         for (int m = tl; m < M; m += CS_CT) P.carry[m] = P.Qtab[(size_t)P.nb * M + m];
 #define val(m) (valb + (size_t)(m) * CT)
     const int s = cs_start(P, blk), e = cs_end(P, blk);
     int32_t *rowc = P.row + (col ? c : 0);
-    const size_t cc = col ? c : 0;                                                 // (stores: cs_store(P, h * M + cc, v))
+    const size_t cc = col ? c : 0;                                                 // (stores: cs_store<MULTI>(P, h * M + cc, v))
     if (PASS == 1) {
         for (int m = 0; m < M; m++) if (own) val(m)[lane] = -1;
     } else {
@@ -231,14 +232,14 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 if (own) { val(c0)[lane] = v0; val(c1)[lane] = v1; val(c2)[lane] = v2; val(c3)[lane] = v3; }
                 if (PASS == 2) {
                     if (col) {
-                        cs_store(P, (size_t)h * M + cc, v0); cs_store(P, (size_t)(h + 1) * M + cc, v1);
-                        cs_store(P, (size_t)(h + 2) * M + cc, v2); cs_store(P, (size_t)(h + 3) * M + cc, v3);
+                        cs_store<MULTI>(P, (size_t)h * M + cc, v0); cs_store<MULTI>(P, (size_t)(h + 1) * M + cc, v1);
+                        cs_store<MULTI>(P, (size_t)(h + 2) * M + cc, v2); cs_store<MULTI>(P, (size_t)(h + 3) * M + cc, v3);
                     }
                 } else if (col) {
-                    if (wrt[i]) cs_store(P, (size_t)h * M + cc, v0);
-                    if (wrt[i + 1]) cs_store(P, (size_t)(h + 1) * M + cc, v1);
-                    if (wrt[i + 2]) cs_store(P, (size_t)(h + 2) * M + cc, v2);
-                    if (wrt[i + 3]) cs_store(P, (size_t)(h + 3) * M + cc, v3);
+                    if (wrt[i]) cs_store<MULTI>(P, (size_t)h * M + cc, v0);
+                    if (wrt[i + 1]) cs_store<MULTI>(P, (size_t)(h + 1) * M + cc, v1);
+                    if (wrt[i + 2]) cs_store<MULTI>(P, (size_t)(h + 2) * M + cc, v2);
+                    if (wrt[i + 3]) cs_store<MULTI>(P, (size_t)(h + 3) * M + cc, v3);
                 }
                 i += 4;
             } else {
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
                 }
                 const int v = c == cr ? h : max(x, y);
                 if (own) val(cr)[lane] = v;
-                if (col && (PASS == 2 || wrt[i])) cs_store(P, (size_t)h * M + cc, v);
+                if (col && (PASS == 2 || wrt[i])) cs_store<MULTI>(P, (size_t)h * M + cc, v);
                 i += 1;
             }
         }
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(CS_CT) k_cs_pass(CsParams P) {
 #pragma unroll
             for (int u = 0; u < 8; u++) l[u] = m0 + u < M ? __ldg(L + m0 + u) : -1;
 #pragma unroll
-            for (int u = 0; u < 8; u++) if (l[u] >= 0) cs_store(P, (size_t)l[u] * M + cc, val(m0 + u)[lane]);
+            for (int u = 0; u < 8; u++) if (l[u] >= 0) cs_store<MULTI>(P, (size_t)l[u] * M + cc, val(m0 + u)[lane]);
         }
     }
 #undef val
