@@ -6,6 +6,7 @@
 #include "swirld_kernels.cuh"
 #include "swirld_cansee.cuh"
 #include "swirld_rounds.cuh"
+#include "swirld_rcluster.cuh"
 #include "swirld_wide.cuh"
 #include "swirld_stream.cuh"
 
@@ -61,6 +62,11 @@ struct sw_engine {
     int32_t *d_Wf = nullptr, *d_cev = nullptr, *d_rbmeta = nullptr, *d_rbtot = nullptr, *d_gchain = nullptr;   // round-batch state
     ulonglong2 *d_sc = nullptr;
     uint8_t *d_res = nullptr;
+    // cluster round kernel (swirld_rcluster.cuh): seq-space rows of the current chunk, hand-over state
+    int32_t *d_rsg = nullptr, *d_rccont = nullptr;
+    size_t rsg_cap = 0;           // events d_rsg holds
+    bool rc_ok = false;           // a 16-CTA cluster with its shared memory can be resident on this device
+    int rc_min_n = 2048;          // shorter chunks go to the grid-wide kernel directly
     RbParams *d_views = nullptr;  // sw_batch_divide_rounds: the views' parameters (owned by the first engine of a batch)
     int views_cap = 0;
     cudaEvent_t view_ev = nullptr;
@@ -411,6 +417,27 @@ int divide_round_batch(sw_engine *e, int first, int n) {
     {
         cudaEvent_t a = get_event(e), b = get_event(e);
         cudaEventRecord(a, e->stream);
+        if (e->rc_ok && n >= e->rc_min_n) {
+            // the chunk inside one thread-block cluster; k_rounds_batch takes over whatever it hands back (normally nothing)
+            if ((size_t)n > e->rsg_cap) {
+                if (e->d_rsg) { CK(cudaStreamSynchronize(e->stream)); CK(cudaFree(e->d_rsg)); e->d_rsg = nullptr; e->rsg_cap = 0; }
+                const size_t want = std::min<size_t>((size_t)e->cap, std::max<size_t>((size_t)n, 1 << 16));
+                CK(dalloc(&e->d_rsg, want * 64));
+                e->rsg_cap = want;
+            }
+            k_rc_seqrows<<<std::max(1, std::min(4 * e->n_sm, (n + 7) / 8)), 256, 0, e->stream>>>(R, e->d_rsg);
+            CK(cudaGetLastError());
+            RcParams Q{R, e->d_rsg, e->d_rccont};
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(RC_CS); cfg.blockDim = dim3(RC_THREADS); cfg.dynamicSmemBytes = RC_SMEM_BYTES; cfg.stream = e->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = RC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster<UNIT>, Q));
+            R.cont = e->d_rccont;
+            e->stats.kernel_launches += 2;
+        }
         CK(cudaLaunchCooperativeKernel((void *)k_rounds_batch<NC, UNIT>, dim3(grid), dim3(RB_THREADS), args, 0, e->stream));
         cudaEventRecord(b, e->stream);
         e->spans.push_back(TimedSpan{a, b, 4});
@@ -567,6 +594,29 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
         } else {
             CK(dalloc(&e->d_sc, cap)); CK(dalloc(&e->d_res, (size_t)2 * 64 * RB_LMAX));
             CK(dalloc(&e->d_SM, cap)); CK(dalloc(&e->d_S, RM));
+            // the cluster round kernel: 16 CTAs with ~174 KB of shared memory each must fit one GPC
+            CK(dalloc(&e->d_rccont, (size_t)132)); CK(cudaMemsetAsync(e->d_rccont, 0, sizeof(int32_t) * 132, e->stream));
+            bool want = true;
+            if (const char *v = getenv("SW_ROUNDS_CLUSTER")) want = atoi(v) != 0;
+            if (const char *v = getenv("SW_RC_MIN_N")) e->rc_min_n = std::max(1, atoi(v));
+            if (want) {
+                int ncl = 0;
+                const void *fn = e->unit ? (const void *)k_rounds_cluster<true> : (const void *)k_rounds_cluster<false>;
+                cudaError_t er = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM_BYTES);
+                if (er == cudaSuccess) er = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (er == cudaSuccess) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(RC_CS); cfg.blockDim = dim3(RC_THREADS); cfg.dynamicSmemBytes = RC_SMEM_BYTES;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = RC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    er = cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg);
+                }
+                e->rc_ok = er == cudaSuccess && ncl >= 1;
+                if (er != cudaSuccess) (void)cudaGetLastError();
+                if (getenv("SW_DEBUG")) fprintf(stderr, "swirld_b200: cluster round kernel %s (%s, %d clusters of %d CTAs resident)\n", e->rc_ok ? "on" : "off", cudaGetErrorString(er), ncl, RC_CS);
+            }
         }
         CK(dalloc(&e->d_round, cap)); CK(dalloc(&e->d_wit, cap)); CK(dalloc(&e->d_famous_ev, cap));
         CK(dalloc(&e->d_W, RM)); CK(dalloc(&e->d_famous, RM));
@@ -629,7 +679,7 @@ void sw_destroy(sw_engine *e) {
                     e->d_round, e->d_wit, e->d_famous_ev, e->d_W, e->d_S, e->d_famous, e->d_consensus,
                     e->d_done, e->d_rem, e->d_newc, e->d_stake, e->d_scal, e->d_lastord, e->d_tx, e->d_idx,
                     e->d_batch_ev, e->d_batch_seg, e->d_perm, e->d_ts, e->d_key, e->d_seg_start, e->d_seg_fw,
-                    e->d_seg_nf, e->d_seg_white, e->d_rounds_in, e->d_plan, e->d_flush};
+                    e->d_seg_nf, e->d_seg_white, e->d_rounds_in, e->d_plan, e->d_flush, e->d_rsg, e->d_rccont};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (e->h_scal) cudaFreeHost(e->h_scal);
     if (e->h_newc) cudaFreeHost(e->h_newc);

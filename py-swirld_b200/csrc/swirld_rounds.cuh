@@ -63,6 +63,8 @@ struct RbParams {
     int32_t *W;                 // [Rcap][M] the reference's witnesses table
     u64 *SM;                    // [cap]
     int32_t *wlist, *wcnt;      // witnesses of the chunk (k_rb_witness -> k_strong)
+    const int32_t *cont;        // NULL, or where k_rounds_cluster (swirld_rcluster.cuh) stopped: [0,64) positions, [64,128) rounds,
+                                // [128] != 0: there is work left
 };
 
 // ---- per-member event lists of the chunk
@@ -152,6 +154,7 @@ __device__ __forceinline__ void rounds_batch_body(const RbParams &P, const int b
     const int gw = bx * (blockDim.x >> 5) + warp, nw = gx * (blockDim.x >> 5);
     const i64 thr = P.tot2 / 3;
     const bool lead = bx == 0;
+    if (P.cont && __ldcg(P.cont + 128) == 0) return;         // the cluster kernel finished the chunk (the same answer in every CTA)
     // per-step results, double buffered: first hit of a chain as (position << 32 | event), first deferred position
     // (three buffers: the tests of step s+1 start without a grid barrier after the bookkeeping of step s)
     u64 *hitmin = reinterpret_cast<u64 *>(P.res);             // [3][64]
@@ -177,7 +180,9 @@ __device__ __forceinline__ void rounds_batch_body(const RbParams &P, const int b
                 cu = pa < 0 ? 0 : P.round[pa];
             }
         }
-        off[c] = o; len[c] = l; pos[c] = 0; cur[c] = cu;
+        int p = 0;
+        if (P.cont && c < M) { p = __ldcg(P.cont + c); cu = __ldcg(P.cont + 64 + c); }
+        off[c] = o; len[c] = l; pos[c] = p; cur[c] = cu;
         cmin_s[c] = c < M ? P.cmin[c] : 0; ctot_s[c] = c < M ? P.ctot[c] : 0;
     }
     if (lead && tid < 192) { hitmin[tid] = ~0ull; unkmin[tid] = 0x7fffffff; }

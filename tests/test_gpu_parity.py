@@ -16,11 +16,18 @@ pytestmark = pytest.mark.gpu
 ALL = list(gs.SPECS)
 
 
-@pytest.fixture(params=["default", "wide"])
+@pytest.fixture(params=["default", "grid", "cluster", "wide"])
 def impl(request, monkeypatch):
-    """Both implementations of the path: the M <= 64 kernels (swirld_rounds.cuh / swirld_kernels.cuh) and the
-    any-M kernels of swirld_wide.cuh, which SW_FORCE_WIDE=1 selects for M <= 64 too (read by sw_create)."""
+    """The implementations of the path (all read by sw_create): "default" = the M <= 64 kernels with the cluster
+    round kernel (swirld_rcluster.cuh) for chunks of >= 2048 events and the grid-wide one (swirld_rounds.cuh) below;
+    "grid" = the grid-wide round kernel only; "cluster" = the cluster round kernel for every batch call; "wide" = the
+    any-M kernels of swirld_wide.cuh, which SW_FORCE_WIDE=1 selects for M <= 64 too."""
     monkeypatch.setenv("SW_FORCE_WIDE", "1" if request.param == "wide" else "0")
+    monkeypatch.setenv("SW_ROUNDS_CLUSTER", "0" if request.param == "grid" else "1")
+    if request.param == "cluster":
+        monkeypatch.setenv("SW_RC_MIN_N", "1")
+    else:
+        monkeypatch.delenv("SW_RC_MIN_N", raising=False)
     return request.param
 
 
@@ -72,6 +79,40 @@ def test_engine_matches_oracle_tick_and_tied(M, N, K, seed, impl):
         o = orc.run_oracle(tr, K)
         r = _run(tr, K)
         assert_same(o, r, what=tr.name)
+
+
+def _late_joiner(M, N, join_at, seed):
+    """Gossip among members 0..M-2; member M-1 creates its root only after `join_at` events (dozens of rounds in):
+    its chain starts more rounds behind than the round kernels mirror in shared memory."""
+    from swirld_b200 import traces
+    rng = np.random.default_rng(seed)
+    p0, p1, cr, head = [], [], [], {}
+    for c in range(M - 1):
+        head[c] = len(cr); p0.append(-1); p1.append(-1); cr.append(c)
+    while len(cr) < N:
+        if len(cr) == join_at:
+            c = M - 1
+            head[c] = len(cr); p0.append(-1); p1.append(-1); cr.append(c)
+            continue
+        act = sorted(head)
+        c = int(act[rng.integers(len(act))])
+        o = int(act[rng.integers(len(act))])
+        if o == c:
+            continue
+        p0.append(head[c]); p1.append(head[o]); cr.append(c)
+        head[c] = len(cr) - 1
+    return traces._finish(M, np.array(p0, np.int32), np.array(p1, np.int32), np.array(cr, np.int32), seed, "late-joiner")
+
+
+@pytest.mark.parametrize("M,N,join_at,K", [(9, 6000, 3000, 6000), (9, 6000, 3000, 2500), (33, 20000, 14000, 4096)])
+def test_engine_late_joiner_hands_over(M, N, join_at, K, impl):
+    """A chain that starts > 32 rounds behind: the cluster round kernel hands the chunk to the grid-wide one."""
+    tr = _late_joiner(M, N, join_at, 77)
+    o = orc.run_oracle(tr, K)
+    assert int(o["round"].max()) > 40
+    r = _run(tr, K)
+    assert_same(o, r, what=tr.name)
+    assert np.array_equal(o["oracle"].can_see(), r["can_see"])
 
 
 def test_engine_stake_and_coin_period(impl):

@@ -15,5 +15,6 @@ for rep in range(1):
     n=max(1,c[6])
     print('cta 0 warp 0: steps %d; cycles per step: prep %.0f  masks %.0f  sync1 %.0f  test %.0f  sync2 %.0f  update %.0f'%((c[6],)+tuple(c[i]/n for i in range(6))))
     print('all warps: tests %d (deferred %d), mean %.0f cycles, max %d; mask misses %d'%(c[11],c[12],c[10]/max(1,c[11]),c[8],c[9]))
+    print('cluster kernel: %d launches, %d handed the rest of their chunk to k_rounds_batch' % (c[7], c[15]))
     print('gather: mean %.0f max %d'%(c[13]/max(1,c[11]), c[14]))
     print('stats', {k:(round(v,2) if isinstance(v,float) else v) for k,v in st.items()})
