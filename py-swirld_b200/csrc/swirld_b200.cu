@@ -67,6 +67,7 @@ struct sw_engine {
     size_t rsg_cap = 0;           // events d_rsg holds
     bool rc_ok = false;           // a 16-CTA cluster with its shared memory can be resident on this device
     int rc_min_n = 2048;          // shorter chunks go to the grid-wide kernel directly
+    RcParams *d_rcviews = nullptr;
     RbParams *d_views = nullptr;  // sw_batch_divide_rounds: the views' parameters (owned by the first engine of a batch)
     int views_cap = 0;
     cudaEvent_t view_ev = nullptr;
@@ -405,6 +406,27 @@ int round_batch_finish(sw_engine *e, const RbParams &R) {
     return 0;
 }
 
+// seq-space rows of the chunk for the cluster round kernel (after round_batch_prep grouped the chunk by creator)
+int rc_seqrows(sw_engine *e, const RbParams &R) {
+    const int n = R.n;
+    if ((size_t)n > e->rsg_cap) {
+        if (e->d_rsg) { CK(cudaStreamSynchronize(e->stream)); CK(cudaFree(e->d_rsg)); e->d_rsg = nullptr; e->rsg_cap = 0; }
+        const size_t want = std::min<size_t>((size_t)e->cap, std::max<size_t>((size_t)n, 1 << 16));
+        CK(dalloc(&e->d_rsg, want * 64));
+        e->rsg_cap = want;
+    }
+    k_rc_seqrows<<<std::max(1, std::min(4 * e->n_sm, (n + 7) / 8)), 256, 0, e->stream>>>(R, e->d_rsg);
+    CK(cudaGetLastError());
+    return 0;
+}
+void rc_launch_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *at, int clusters, cudaStream_t stream) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(RC_CS * clusters); cfg.blockDim = dim3(RC_THREADS); cfg.dynamicSmemBytes = RC_SMEM_BYTES; cfg.stream = stream;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = RC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+}
+
 template <int NC, bool UNIT>
 int divide_round_batch(sw_engine *e, int first, int n) {
     // a few SMs stay free for the can_see scan of the next chunk, which runs beside this kernel (SW_RB_FREE_SMS)
@@ -419,21 +441,11 @@ int divide_round_batch(sw_engine *e, int first, int n) {
         cudaEventRecord(a, e->stream);
         if (e->rc_ok && n >= e->rc_min_n) {
             // the chunk inside one thread-block cluster; k_rounds_batch takes over whatever it hands back (normally nothing)
-            if ((size_t)n > e->rsg_cap) {
-                if (e->d_rsg) { CK(cudaStreamSynchronize(e->stream)); CK(cudaFree(e->d_rsg)); e->d_rsg = nullptr; e->rsg_cap = 0; }
-                const size_t want = std::min<size_t>((size_t)e->cap, std::max<size_t>((size_t)n, 1 << 16));
-                CK(dalloc(&e->d_rsg, want * 64));
-                e->rsg_cap = want;
-            }
-            k_rc_seqrows<<<std::max(1, std::min(4 * e->n_sm, (n + 7) / 8)), 256, 0, e->stream>>>(R, e->d_rsg);
-            CK(cudaGetLastError());
+            if (rc_seqrows(e, R) < 0) return SW_E_CUDA;
             RcParams Q{R, e->d_rsg, e->d_rccont};
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(RC_CS); cfg.blockDim = dim3(RC_THREADS); cfg.dynamicSmemBytes = RC_SMEM_BYTES; cfg.stream = e->stream;
+            cudaLaunchConfig_t cfg;
             cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = RC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
+            rc_launch_config(cfg, at, 1, e->stream);
             CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster<UNIT>, Q));
             R.cont = e->d_rccont;
             e->stats.kernel_launches += 2;
@@ -605,13 +617,13 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
                 cudaError_t er = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM_BYTES);
                 if (er == cudaSuccess) er = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
                 if (er == cudaSuccess) {
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3(RC_CS); cfg.blockDim = dim3(RC_THREADS); cfg.dynamicSmemBytes = RC_SMEM_BYTES;
+                    const void *fv = e->unit ? (const void *)k_rounds_cluster_views<true> : (const void *)k_rounds_cluster_views<false>;
+                    er = cudaFuncSetAttribute(fv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM_BYTES);
+                    if (er == cudaSuccess) er = cudaFuncSetAttribute(fv, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                    cudaLaunchConfig_t cfg;
                     cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeClusterDimension;
-                    at[0].val.clusterDim.x = RC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                    cfg.attrs = at; cfg.numAttrs = 1;
-                    er = cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg);
+                    rc_launch_config(cfg, at, 1, nullptr);
+                    if (er == cudaSuccess) er = cudaOccupancyMaxActiveClusters(&ncl, fv, &cfg);
                 }
                 e->rc_ok = er == cudaSuccess && ncl >= 1;
                 if (er != cudaSuccess) (void)cudaGetLastError();
@@ -666,6 +678,7 @@ void sw_destroy(sw_engine *e) {
     if (e->scan_ev) cudaEventDestroy(e->scan_ev);
     if (e->view_ev) cudaEventDestroy(e->view_ev);
     if (e->d_views) cudaFree(e->d_views);
+    if (e->d_rcviews) cudaFree(e->d_rcviews);
     for (auto ev : e->stage_ev) if (ev) cudaEventDestroy(ev);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->d_stage) cudaFree(e->d_stage);
@@ -895,10 +908,16 @@ int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, c
     const int per_launch = std::max(1, e->n_sm / gmin);
     if (B > e->views_cap) {
         if (e->d_views) cudaFree(e->d_views);
-        e->d_views = nullptr;
+        if (e->d_rcviews) cudaFree(e->d_rcviews);
+        e->d_views = nullptr; e->d_rcviews = nullptr;
         CK(cudaMalloc((void **)&e->d_views, sizeof(RbParams) * B));
+        CK(cudaMalloc((void **)&e->d_rcviews, sizeof(RcParams) * B));
         e->views_cap = B;
     }
+    // one thread-block cluster per view first (swirld_rcluster.cuh); the grid-wide kernel then takes what they hand back
+    bool use_rc = true;
+    for (int v = 0; v < B; v++) use_rc = use_rc && engines[v]->rc_ok && n[v] >= e->rc_min_n;
+    std::vector<RcParams> Qv(B);
     if (!e->view_ev) CK(cudaEventCreateWithFlags(&e->view_ev, cudaEventDisableTiming));
     std::vector<RbParams> Rv(B);
     for (int v0 = 0; v0 < B; v0 += per_launch) {
@@ -913,6 +932,12 @@ int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, c
             } else if (wait_appends(x, first[v] + n[v]) < 0) return SW_E_CUDA;
             // a view's window stays a round deep (16 pending events per chain) however few warps it has: they loop
             if (round_batch_prep(x, first[v], n[v], G, Rv[v], 16) < 0) { e->err = x->err; return SW_E_CUDA; }
+            if (use_rc) {
+                if (rc_seqrows(x, Rv[v]) < 0) { e->err = x->err; return SW_E_CUDA; }
+                Qv[v] = RcParams{Rv[v], x->d_rsg, x->d_rccont};
+                Rv[v].cont = x->d_rccont;
+                x->stats.kernel_launches += 1;
+            }
             cudaEvent_t ev = get_event(x);
             CK(cudaEventRecord(ev, x->stream));
             CK(cudaStreamWaitEvent(e->stream, ev, 0));
@@ -925,6 +950,16 @@ int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, c
         {
             cudaEvent_t a = get_event(e), b = get_event(e);
             cudaEventRecord(a, e->stream);
+            if (use_rc) {
+                CK(cudaMemcpyAsync(e->d_rcviews + v0, Qv.data() + v0, sizeof(RcParams) * nv, cudaMemcpyHostToDevice, e->stream));
+                cudaLaunchConfig_t cfg;
+                cudaLaunchAttribute at[1];
+                rc_launch_config(cfg, at, nv, e->stream);
+                const RcParams *qv = e->d_rcviews + v0;
+                if (e->unit) CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster_views<true>, qv));
+                else CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster_views<false>, qv));
+                e->stats.kernel_launches += 1;
+            }
             void *fn = e->NC == 1 ? (e->unit ? (void *)k_rounds_batch_views<1, true> : (void *)k_rounds_batch_views<1, false>)
                                   : (e->unit ? (void *)k_rounds_batch_views<2, true> : (void *)k_rounds_batch_views<2, false>);
             CK(cudaLaunchCooperativeKernel(fn, dim3(nv * G), dim3(RB_THREADS), args, 0, e->stream));

@@ -108,7 +108,7 @@ __device__ __forceinline__ void rc_vadd_xor(u64 (&a)[8], int delta) {
 }
 
 template <bool UNIT>
-__global__ void __launch_bounds__(RC_THREADS, 1) k_rounds_cluster(RcParams Q) {
+__device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     const RbParams &P = Q.R;
     extern __shared__ __align__(16) unsigned char rc_smem[];
     int (*rsw)[RC_WN][64] = reinterpret_cast<int (*)[RC_WN][64]>(rc_smem);                       // [chain][slot][member]
@@ -516,4 +516,17 @@ __global__ void __launch_bounds__(RC_THREADS, 1) k_rounds_cluster(RcParams Q) {
         atomicAdd(&o[15], (unsigned long long)handed);
     }
     rc_cluster_sync();                                          // nobody leaves while its shared memory may still be written
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(RC_THREADS, 1) k_rounds_cluster(RcParams Q) { rounds_cluster_body<UNIT>(Q); }
+
+// several independent node-views (swirld_rounds.cuh, k_rounds_batch_views): one cluster per view, as many side by side
+// as the device holds -- the clusters never talk to each other, so this is an ordinary (non-cooperative) launch
+template <bool UNIT>
+__global__ void __launch_bounds__(RC_THREADS, 1) k_rounds_cluster_views(const RcParams *Qv) {
+    __shared__ RcParams Qs;
+    if (threadIdx.x == 0) Qs = Qv[blockIdx.x / RC_CS];
+    __syncthreads();
+    rounds_cluster_body<UNIT>(Qs);
 }

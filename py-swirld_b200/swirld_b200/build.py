@@ -11,8 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libswirld_b200.so")
 SOURCES = ["swirld_b200.cu"]
-DEPS = ["swirld_b200.cu", "swirld_kernels.cuh", "swirld_cansee.cuh", "swirld_rounds.cuh", "swirld_wide.cuh", "swirld_stream.cuh",
-        "../../include/swirld_b200.h"]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + ["../../include/swirld_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
