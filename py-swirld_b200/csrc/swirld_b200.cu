@@ -66,6 +66,7 @@ struct sw_engine {
     int32_t *d_rsg = nullptr, *d_rccont = nullptr;
     size_t rsg_cap = 0;           // events d_rsg holds
     bool rc_ok = false;           // a 16-CTA cluster with its shared memory can be resident on this device
+    bool rc_mb = true;            // its exchanges by st.async + mbarrier (SW_RC_MB=0: plain stores + cluster barriers)
     int rc_min_n = 2048;          // shorter chunks go to the grid-wide kernel directly
     RcParams *d_rcviews = nullptr;
     RbParams *d_views = nullptr;  // sw_batch_divide_rounds: the views' parameters (owned by the first engine of a batch)
@@ -205,7 +206,7 @@ int device_error(sw_engine *e) {     // after a sync: did a kernel flag an error
         const char *what = code == SW_E_CAPACITY ? "round table exhausted"
                          : code == SW_E_INDEX ? "list index out of range (swirld.py:305: a single seer)"
                          : code == SW_E_KEY ? "KeyError (undecided witness in a consensus round)"
-                         : code == SW_E_CUDA ? "a peer GPU did not publish its round step in time (multi-GPU exchange)" : "device error";
+                         : code == SW_E_CUDA ? "an exchange inside the round kernel timed out (a peer GPU, or a CTA of the cluster kernel, did not publish its step)" : "device error";
         return fail(e, code, "%s", what);
     }
     return 0;
@@ -446,7 +447,8 @@ int divide_round_batch(sw_engine *e, int first, int n) {
             cudaLaunchConfig_t cfg;
             cudaLaunchAttribute at[1];
             rc_launch_config(cfg, at, 1, e->stream);
-            CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster<UNIT>, Q));
+            if (e->rc_mb) CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster<UNIT, true>, Q));
+            else CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster<UNIT, false>, Q));
             R.cont = e->d_rccont;
             e->stats.kernel_launches += 2;
         }
@@ -613,11 +615,14 @@ int sw_create(int M, int capacity_events, const int64_t *stake, int coin_period,
             if (const char *v = getenv("SW_RC_MIN_N")) e->rc_min_n = std::max(1, atoi(v));
             if (want) {
                 int ncl = 0;
-                const void *fn = e->unit ? (const void *)k_rounds_cluster<true> : (const void *)k_rounds_cluster<false>;
+                if (const char *v = getenv("SW_RC_MB")) e->rc_mb = atoi(v) != 0;
+                const void *fn = e->unit ? (e->rc_mb ? (const void *)k_rounds_cluster<true, true> : (const void *)k_rounds_cluster<true, false>)
+                                         : (e->rc_mb ? (const void *)k_rounds_cluster<false, true> : (const void *)k_rounds_cluster<false, false>);
                 cudaError_t er = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM_BYTES);
                 if (er == cudaSuccess) er = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
                 if (er == cudaSuccess) {
-                    const void *fv = e->unit ? (const void *)k_rounds_cluster_views<true> : (const void *)k_rounds_cluster_views<false>;
+                    const void *fv = e->unit ? (e->rc_mb ? (const void *)k_rounds_cluster_views<true, true> : (const void *)k_rounds_cluster_views<true, false>)
+                                             : (e->rc_mb ? (const void *)k_rounds_cluster_views<false, true> : (const void *)k_rounds_cluster_views<false, false>);
                     er = cudaFuncSetAttribute(fv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM_BYTES);
                     if (er == cudaSuccess) er = cudaFuncSetAttribute(fv, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
                     cudaLaunchConfig_t cfg;
@@ -916,7 +921,7 @@ int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, c
     }
     // one thread-block cluster per view first (swirld_rcluster.cuh); the grid-wide kernel then takes what they hand back
     bool use_rc = true;
-    for (int v = 0; v < B; v++) use_rc = use_rc && engines[v]->rc_ok && n[v] >= e->rc_min_n;
+    for (int v = 0; v < B; v++) use_rc = use_rc && engines[v]->rc_ok && engines[v]->rc_mb == e->rc_mb && n[v] >= e->rc_min_n;
     std::vector<RcParams> Qv(B);
     if (!e->view_ev) CK(cudaEventCreateWithFlags(&e->view_ev, cudaEventDisableTiming));
     std::vector<RbParams> Rv(B);
@@ -956,8 +961,8 @@ int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, c
                 cudaLaunchAttribute at[1];
                 rc_launch_config(cfg, at, nv, e->stream);
                 const RcParams *qv = e->d_rcviews + v0;
-                if (e->unit) CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster_views<true>, qv));
-                else CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster_views<false>, qv));
+                if (e->unit) { if (e->rc_mb) CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster_views<true, true>, qv)); else CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster_views<true, false>, qv)); }
+                else { if (e->rc_mb) CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster_views<false, true>, qv)); else CK(cudaLaunchKernelEx(&cfg, k_rounds_cluster_views<false, false>, qv)); }
                 e->stats.kernel_launches += 1;
             }
             void *fn = e->NC == 1 ? (e->unit ? (void *)k_rounds_batch_views<1, true> : (void *)k_rounds_batch_views<1, false>)

@@ -4,25 +4,33 @@
 // swirld_rounds.cuh advances all member chains one round per grid-wide step; a step there is ~8 dependent trips
 // through L2 (rows, mask cache, atomics, the grid barrier, the results): 6 us, 1461 times per million events.  The
 // work of a step is small (a few thousand masks and tests), so this kernel keeps everything a step touches in the
-// shared memory of 16 CTAs and pays distributed-shared-memory latency (~200 cycles) and two cluster barriers instead:
+// shared memory of 16 CTAs and moves it over distributed shared memory (~200 cycles a hop):
 //
 //   * rows in SEQ space: rs(h)[c] = the chain position (swirld.py's implicit per-creator sequence number) of the
 //     event of member c that h sees (k_rc_seqrows, from the can_see table).  Every comparison of the scheme
 //     ("row(k)[c_] >= Wf_r[c_]") holds in seq space as it does in index space -- a member's events are ordered the
 //     same way in both -- and a mask S_r(k) is addressed by (member, position) without any lookup.
-//   * CTA q owns chains 4q..4q+3: a window of RC_WN consecutive rows per chain in its shared memory, filled one
-//     step ahead by cp.async.
+//   * CTA q owns chains 4q..4q+3: a window of RC_WN consecutive rows per chain (and their event indices) in its
+//     shared memory, filled one step ahead by cp.async.  The state of chain c (position, round, window bounds) lives
+//     in the registers of thread c of EVERY CTA: all 16 CTAs do the same bookkeeping from the same results, so no
+//     decision ever has to be communicated.
 //   * a step (round r = lowest open round):
-//       a  the owner computes S_r of its members' events [Wls_r[m], mend[m]) from its window and stores each mask
-//          into the mask table of ALL 16 CTAs (st.shared::cluster);                       cluster barrier
-//       b  the owner finds each chain's first pending event that passes P_r: P_r, and "an event that sees beyond
-//          the prepared masks", are monotone along a chain, so a 5-ary search with the chain's 4 warps needs 3
-//          passes of one test per warp (the test of swirld_rounds.cuh, masks from LOCAL shared memory);
-//       c  the results go to every CTA (64 words);                                       cluster barrier
-//       d  identical bookkeeping in every CTA (positions, rounds, the seq-space mirror of Wf), the owner stores the
-//          final rounds, the window slides.
+//       a  the owner computes S_r of its members' events [Wls_r[m], mend[m]) from its window into its own mask table
+//          and sends each member's masks to the other 15 tables as 16-byte st.async stores, which count their bytes
+//          on an mbarrier of the receiver (the receiver knows how many bytes to expect: it does the same arithmetic);
+//       b  the owner finds each chain's first pending event that passes P_r (1) or sees beyond the prepared masks (2):
+//          unit stake: all 32 positions of the window at once, 8 tests per warp, 4 lanes x 16 members per test --
+//          a lane adds the masks of its live members into a bit-sliced (vertical) counter with carry-save adders,
+//          the 4 lanes add their counters by shuffles, and the 64 column counts are compared with the threshold
+//          plane by plane; what needs only the CTA's own rows runs before the wait for the others' masks.
+//          Integer stakes: a 5-ary search with the chain's 4 warps (P_r and "beyond the masks" are monotone along
+//          a chain), one test of swirld_rounds.cuh's kind per warp and pass;
+//       c  (first position, kind) of every chain to every CTA, again by st.async + mbarrier;
+//       d  identical bookkeeping in every CTA; the owner stores the final rounds and Wf, the window slides.
+//     With MB = false the two exchanges use plain DSMEM stores and barrier.cluster instead (the release fence of the
+//     barrier also waits for the step's global stores: slower; kept for A/B, SW_RC_MB=0).
 //   * whatever the windows cannot decide -- no progress for RC_STALL steps, a chain more than RB_WR rounds behind,
-//     rows further before the chunk than the ring -- hands the REST of the chunk to k_rounds_batch through `cont`
+//     rows further before the chunk than RC_REACH -- hands the REST of the chunk to k_rounds_batch through `cont`
 //     (positions and rounds per chain).  tests/test_rounds_cluster_model.py is the executable model.
 #pragma once
 #include "swirld_rounds.cuh"
@@ -39,6 +47,7 @@
 #define RC_STALL 3
 #define RC_REACH (RC_WN / 2) // rows before the chunk that a launch may need (from the ring)
 #define RC_INF 0x7fffffff
+#define RC_BIG 0x3fffffff    // "no event of this round": above every chain position
 
 struct RcParams {
     RbParams R;
@@ -47,9 +56,9 @@ struct RcParams {
 };
 
 #define RC_SMEM_ROWS ((size_t)RC_CPC * RC_WN * 64 * 4)
-#define RC_SMEM_MASK ((size_t)64 * RC_MR * 8)
+#define RC_SMEM_MASK ((size_t)2 * 64 * RC_MR * 8)   // two mask tables: a CTA may receive the next step's masks while it still tests
 #define RC_SMEM_WLS ((size_t)RB_WR * 64 * 4)
-#define RC_SMEM_BYTES (RC_SMEM_ROWS + RC_SMEM_MASK + RC_SMEM_WLS + 512 + 8192)
+#define RC_SMEM_BYTES (RC_SMEM_ROWS + RC_SMEM_MASK + RC_SMEM_WLS + 512 + 10240)
 
 // seq-space rows of the chunk, grouped by creator like cev: one warp per event
 __global__ void __launch_bounds__(256) k_rc_seqrows(RbParams P, int32_t *rsg) {
@@ -66,9 +75,9 @@ __global__ void __launch_bounds__(256) k_rc_seqrows(RbParams P, int32_t *rsg) {
 }
 
 __device__ __forceinline__ unsigned rc_cta_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void rc_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+__device__ __forceinline__ void rc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void rc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void rc_cluster_sync() { rc_cluster_arrive(); rc_cluster_wait(); }
 __device__ __forceinline__ unsigned rc_map(const void *p, unsigned rank) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(p);
     unsigned r;
@@ -107,21 +116,50 @@ __device__ __forceinline__ void rc_vadd_xor(u64 (&a)[8], int delta) {
     a[NB] = carry;
 }
 
-template <bool UNIT>
+// ---- message passing without fences: st.async delivers the data AND counts its bytes on an mbarrier of the receiving CTA
+__device__ __forceinline__ void rc_mbar_init(unsigned mbar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void rc_mbar_expect(unsigned mbar, unsigned bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" :: "r"(mbar), "r"(bytes) : "memory");
+}
+// false: the bytes did not arrive within ~0.2 s (a bug or a dead peer CTA; the caller gives up instead of hanging the GPU)
+__device__ __forceinline__ bool rc_mbar_wait(unsigned mbar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return true;
+        if (clock64() - t0 > 400000000ll) return false;
+    }
+}
+__device__ __forceinline__ void rc_sta_v4(unsigned addr, uint4 v, unsigned mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void rc_sta_u32(unsigned addr, unsigned v, unsigned mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" :: "r"(addr), "r"(v), "r"(mbar) : "memory");
+}
+
+// MB: the two exchanges of a step (masks, results) by st.async + mbarrier instead of stores + cluster barriers
+template <bool UNIT, bool MB>
 __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     const RbParams &P = Q.R;
     extern __shared__ __align__(16) unsigned char rc_smem[];
     int (*rsw)[RC_WN][64] = reinterpret_cast<int (*)[RC_WN][64]>(rc_smem);                       // [chain][slot][member]
-    u64 (*maskbuf)[RC_MR] = reinterpret_cast<u64 (*)[RC_MR]>(rc_smem + RC_SMEM_ROWS);            // [member][offset]
+    u64 (*maskbuf0)[RC_MR] = reinterpret_cast<u64 (*)[RC_MR]>(rc_smem + RC_SMEM_ROWS);           // [2][member][offset]
     int (*Wls)[64] = reinterpret_cast<int (*)[64]>(rc_smem + RC_SMEM_ROWS + RC_SMEM_MASK);       // seq of Wf_r[c], -1: none
     i64 *stake_s = reinterpret_cast<i64 *>(rc_smem + RC_SMEM_ROWS + RC_SMEM_MASK + RC_SMEM_WLS);
     int *iv = reinterpret_cast<int *>(stake_s + 64);
-    int *cur = iv, *pos = iv + 64, *len = iv + 128, *off = iv + 192, *cmin_s = iv + 256, *ctot_s = iv + 320;
-    int *wlo = iv + 384, *wld = iv + 448, *wrd = iv + 512, *slo = iv + 576, *smend = iv + 640, *swin = iv + 704;
-    int *xres = iv + 768, *s_nfin = iv + 832, *s_base = iv + 896, *s_old = iv + 960, *coff_s = iv + 1024;
-    int *sa = iv + 1088, *sb = sa + RC_CPC, *svb = sb + RC_CPC, *tres = svb + RC_CPC;             // tres[RC_CPC][RC_WPC]
+    // what the chain threads (tid < 64, one per member chain) publish for the other warps, per step
+    int *slo = iv, *smend = iv + 64, *swin = iv + 128, *spos = iv + 192, *s_old = iv + 256, *wldp = iv + 320;
+    int *s_nfin = iv + 384, *s_base = iv + 448, *xres = iv + 512, *wp = iv + 576, *cnts = iv + 640;
+    // constants of the launch
+    int *off = iv + 704, *cmin_s = iv + 768, *coff_s = iv + 832, *len_s = iv + 896, *ctot_s = iv + 960, *cur0 = iv + 1024;
+    int *ws = iv + 1088;                                                                         // [8] warp results
+    int *sa = iv + 1096, *sb = sa + RC_CPC, *svb = sb + RC_CPC, *tres = svb + RC_CPC;             // tres[RC_CPC][RC_WPC]
     int (*cevw)[RC_WN] = reinterpret_cast<int (*)[RC_WN]>(iv + 1152);                           // event index of every window row
     int *vres = iv + 1152 + RC_CPC * RC_WN;                                                      // [RC_CPC][RC_LW] test results
+    int2 (*cst)[64] = reinterpret_cast<int2 (*)[64]>(iv + 1792);                                 // [chain][member] {threshold, span}
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(iv + 2304);                        // mbarriers: masks (2 tables), results
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M;
@@ -136,64 +174,58 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
         const int w = (c < M && r >= 0 && r < P.Rcap) ? __ldcg(P.Wf + (size_t)r * M + c) : -1;
         Wls[slot][c] = w >= 0 ? P.seq[w] : -1;
     }
+    // ---- the state of chain c lives in the registers of thread c
+    int my_pos = 0, my_cur = RC_INF, my_len = 0, my_cmin = 0, my_ctot = 0, my_wlo = 0, my_wld = 0, my_wrd = 0;
+    bool my_tested = false;
     if (tid < 64) {
         const int c = tid;
         stake_s[c] = c < M ? P.stake[c] : 0;
-        int o = 0, l = 0, cu = RC_INF, co = 0;
+        int o = 0, co = 0;
+        bool root = false;
         if (c < M) {
-            co = P.coff[c]; o = P.first + co; l = P.coff[c + 1] - co;
-            if (l > 0) {
+            co = P.coff[c]; o = P.first + co; my_len = P.coff[c + 1] - co;
+            my_ctot = P.ctot[c];
+            if (my_len > 0) {
                 const int h0 = P.cev[o], pa = P.p0[h0];
-                cu = pa < 0 ? 0 : P.round[pa];
+                my_cur = pa < 0 ? 0 : P.round[pa];
+                my_cmin = P.cmin[c];
+                root = pa < 0;
+                if (root && lead) P.Wf[c] = h0;                 // a member's root opens round 0 for it
             }
         }
-        off[c] = o; len[c] = l; pos[c] = 0; cur[c] = cu; coff_s[c] = co;
-        cmin_s[c] = (c < M && l > 0) ? P.cmin[c] : 0; ctot_s[c] = c < M ? P.ctot[c] : 0;
+        off[c] = o; coff_s[c] = co; cmin_s[c] = my_cmin; len_s[c] = my_len; ctot_s[c] = my_ctot; cur0[c] = my_cur;
+        xres[c] = root ? 1 : 0;
     }
     __syncthreads();
-    if (tid < M && len[tid] > 0 && cur[tid] == 0) {            // a member's root opens round 0 for it
-        const int h0 = P.cev[off[tid]];
-        if (P.p0[h0] < 0) {
-            if (rtop < RB_WR) Wls[0][tid] = 0;
-            if (lead) P.Wf[tid] = h0;
-        }
-    }
+    if (tid < 64 && xres[tid] && rtop < RB_WR) Wls[0][tid] = 0;
     __syncthreads();
 
-    auto lowest_open = [&]() -> int {                           // every warp for itself: the state is identical in all CTAs
-        int r = RC_INF;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int c = lane + 32 * j;
-            if (pos[c] < len[c]) r = min(r, cur[c]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o));
-        return r;
-    };
-    auto seqpos = [&](int c) -> int { return len[c] > 0 ? cmin_s[c] + pos[c] : ctot_s[c]; };
-
+    if (MB && tid == 0) {
+        rc_mbar_init(mbar0, 1); rc_mbar_init(mbar0 + 8, 1); rc_mbar_init(mbar0 + 16, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     int handed = 0;
     // ---- the windows at launch: [wlo, wld) from the chunk's seq rows, what precedes the chunk through the ring
     {
-        const int rmin = lowest_open();
-        bool bad = false;
-        if (rmin != RC_INF && rmin <= rtop - RB_WR) bad = true;
-        if (tid < 64 && rmin != RC_INF && !bad) {
-            const int c = tid, sp = seqpos(c);
-            const int lo = Wls[rmin & (RB_WR - 1)][c];
-            const int wl = lo >= 0 ? min(lo, sp) : sp;
-            const int before = len[c] > 0 ? cmin_s[c] : ctot_s[c];
-            if (before - wl > RC_REACH) bad = true;
-            wlo[c] = wl;
-            wld[c] = wrd[c] = min(min(ctot_s[c], wl + RC_WN), sp + RC_LW + RC_PF);
+        int r0 = RC_INF;
+#pragma unroll
+        for (int j = 0; j < 2; j++) if (len_s[lane + 32 * j] > 0) r0 = min(r0, cur0[lane + 32 * j]);
+        r0 = __reduce_min_sync(0xffffffffu, r0);
+        bool bad = r0 != RC_INF && r0 <= rtop - RB_WR;
+        if (tid < 64 && r0 != RC_INF && !bad) {
+            const int sp = my_len > 0 ? my_cmin : my_ctot;     // (also: where the chunk's events of this chain begin)
+            const int lo = Wls[r0 & (RB_WR - 1)][tid];
+            my_wlo = lo >= 0 ? min(lo, sp) : sp;
+            if (sp - my_wlo > RC_REACH) bad = true;
+            my_wld = my_wrd = min(min(my_ctot, my_wlo + RC_WN), sp + RC_LW + RC_PF);
+            s_old[tid] = my_wlo; wldp[tid] = my_wld;
         }
         if (__syncthreads_or(bad)) handed = 1;
-        if (!handed && rmin != RC_INF) {
+        if (!handed && r0 != RC_INF) {
             for (int cl = 0; cl < RC_CPC; cl++) {
                 const int c = bx * RC_CPC + cl;
-                const int before = len[c] > 0 ? cmin_s[c] : ctot_s[c];
-                for (int sq = wlo[c] + warp; sq < wld[c]; sq += RC_THREADS / 32) {
+                const int before = len_s[c] > 0 ? cmin_s[c] : ctot_s[c];
+                for (int sq = s_old[c] + warp; sq < wldp[c]; sq += RC_THREADS / 32) {
                     int v0, v1;
                     if (sq >= before) {
                         const int32_t *src = Q.rsg + (size_t)(coff_s[c] + sq - cmin_s[c]) * 64;
@@ -214,133 +246,220 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     rc_cluster_sync();                                          // every CTA of the cluster runs before any remote store
 
     long long c_t[6] = {0, 0, 0, 0, 0, 0}, c_steps = 0, c_tests = 0, c_unk = 0;
-    int stall = 0;
-    while (!handed) {
+    int stall = 0, rmin = 0;
+    bool have_res = false;
+    unsigned it = 0;                                            // steps so far (mbarrier phases)
+    for (; !handed; ++it) {
         const long long t0 = clock64();
-        const int rmin = lowest_open();
-        if (rmin == RC_INF) break;                              // every chain is done
-        if (rmin <= rtop - RB_WR) { handed = 1; break; }
-        const int slot = rmin & (RB_WR - 1);
-        if (tid < 64) {
-            const int c = tid, lo = Wls[slot][c], sp = seqpos(c);
-            const bool open = pos[c] < len[c];
-            int me = -1;
-            if (lo >= 0) me = min(min(wrd[c], open ? sp + RC_LW : ctot_s[c]), lo + RC_MR);
-            slo[c] = lo; smend[c] = me;
-            swin[c] = (open && cur[c] == rmin) ? max(0, min(min(RC_LW, len[c] - pos[c]), wrd[c] - sp)) : -1;
+        u64 (*maskbuf)[RC_MR] = maskbuf0 + (MB ? (it & 1) * 64 : 0);
+        // ---- the results of the last step (every CTA holds all of them): positions, rounds, the mirror of Wf
+        bool late = false;
+        if (MB) {
+            if (have_res) late = !rc_mbar_wait(mbar0 + 16, (it - 1) & 1);
+            if (tid == 0) rc_mbar_expect(mbar0 + 16, 64 * 4);  // this step's results: one word per chain
         }
-        __syncthreads();
-        const long long t1 = clock64();
-        // ---- a: the masks of my members' ranges into my own table, then each member's masks to every other CTA as
-        //         one wide store per (member, CTA)
-        {
-            const int w0 = slo[lane], w1 = slo[lane + 32];
-            int cnt[RC_CPC], total = 0;
-#pragma unroll
-            for (int cl = 0; cl < RC_CPC; cl++) {
-                const int c = bx * RC_CPC + cl;
-                cnt[cl] = max(0, smend[c] - slo[c]);
-                total += cnt[cl];
+        asm volatile("cp.async.wait_all;" ::: "memory");        // (the rows issued a step ago)
+        int nf = 0, base = 0, hitseq = -1;
+        bool hit = false, prog = false;
+        if (tid < 64) {
+            if (have_res && my_tested) {
+                const int x = xres[tid], f = x >> 2, vf = x & 3;
+                base = my_cmin + my_pos; nf = f;
+                if (vf == 1) { hit = true; my_cur = rmin + 1; hitseq = base + f; }
+                my_pos += f;
+                prog = f > 0 || vf == 1;
             }
-            for (int item = warp; item < total; item += RC_THREADS / 32) {
-                int cl = 0, i = item;
+            s_nfin[tid] = nf; s_base[tid] = base;
+        }
+        if (warp < 2) {
+            const int cm = __reduce_min_sync(0xffffffffu, my_pos < my_len ? my_cur : RC_INF);
+            const int fl = (__any_sync(0xffffffffu, hit) ? 1 : 0) | (__any_sync(0xffffffffu, prog) ? 2 : 0);
+            if (lane == 0) { ws[2 * warp] = cm; ws[2 * warp + 1] = fl; }
+        }
+        if (__syncthreads_or(late)) {                           // (never, unless a peer CTA died)
+            if (tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -4);
+            handed = 1;
+            break;
+        }
+        const int rnext = min(ws[0], ws[2]), fl = ws[1] | ws[3];  // lowest open round; any hit / any progress
+        bool newrow = false;
+        if (have_res && (fl & 1) && rmin + 1 > rtop) {          // the hits open the mirror row of round rmin+1
+            rtop = rmin + 1; newrow = true;
+            if (rtop >= P.Rcap && tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -5);
+        }
+        if (tid < 64) {                                         // (each thread its own column)
+            if (hit && rmin + 1 < P.Rcap) {
+                Wls[(rmin + 1) & (RB_WR - 1)][tid] = hitseq;
+                if (tid / RC_CPC == bx) P.Wf[(size_t)(rmin + 1) * M + tid] = cevw[tid % RC_CPC][hitseq & (RC_WN - 1)];
+            } else if (newrow) Wls[rtop & (RB_WR - 1)][tid] = -1;
+        }
+        if (have_res && tid < RC_CPC * RC_LW) {                 // final rounds of my chains' events before the first hit
+            const int cl = tid / RC_LW, j = tid % RC_LW, c = bx * RC_CPC + cl;
+            if (j < s_nfin[c]) P.round[cevw[cl][(s_base[c] + j) & (RC_WN - 1)]] = rmin;
+        }
+        if (rnext == RC_INF) break;                             // every chain is done
+        if (rnext <= rtop - RB_WR) { handed = 1; break; }
+        // ---- this step's ranges and windows
+        bool moved = false;
+        if (tid < 64) {
+            const int c = tid, sp = my_len > 0 ? my_cmin + my_pos : my_ctot;
+            moved = my_wrd != my_wld;
+            my_wrd = my_wld;
+            const int lo = Wls[rnext & (RB_WR - 1)][c];
+            my_wlo = max(my_wlo, lo >= 0 ? min(lo, sp) : sp);
+            const int hi = min(min(my_ctot, my_wlo + RC_WN), sp + RC_LW + RC_PF), old = my_wld;
+            if (hi > my_wld) { my_wld = hi; moved = true; }
+            const bool open = my_pos < my_len;
+            const int me = lo >= 0 ? min(min(my_wrd, open ? sp + RC_LW : my_ctot), lo + RC_MR) : -1;
+            my_tested = open && my_cur == rnext;
+            slo[c] = lo; smend[c] = me; spos[c] = sp; s_old[c] = old; wldp[c] = my_wld;
+            swin[c] = my_tested ? max(0, min(min(RC_LW, my_len - my_pos), my_wrd - sp)) : -1;
+            cnts[c] = lo >= 0 ? max(0, me - lo) : 0;
+            wp[c] = lo >= 0 ? lo : RC_BIG;
+        }
+        if (warp < 2) { const bool am = __any_sync(0xffffffffu, moved); if (lane == 0) ws[4 + warp] = am ? 1 : 0; }
+        __syncthreads();
+        if (have_res) stall = ((fl & 2) || ws[4] || ws[5]) ? 0 : stall + 1;
+        if (stall >= RC_STALL) { handed = 1; break; }
+        rmin = rnext;
+        if (MB && warp == 0) {                                  // the bytes the other CTAs will store into my mask table
+            int by = 0;
 #pragma unroll
-                for (int q = 0; q < RC_CPC - 1; q++) if (cl == q && i >= cnt[q]) { i -= cnt[q]; cl = q + 1; }
-                const int c = bx * RC_CPC + cl, s = slo[c] + i;
-                const int *row = rsw[cl][s & (RC_WN - 1)];
-                const int v0 = row[lane], v1 = row[lane + 32];
-                const u64 mask = (u64)__ballot_sync(0xffffffffu, w0 >= 0 && v0 >= w0) |
-                                 (u64)__ballot_sync(0xffffffffu, w1 >= 0 && v1 >= w1) << 32;
-                if (lane == 0) maskbuf[c][i] = mask;
+            for (int j = 0; j < 2; j++) { const int m = lane + 32 * j; if (m / RC_CPC != bx) by += ((cnts[m] + 1) >> 1) * 16; }
+            by = __reduce_add_sync(0xffffffffu, by);
+            if (lane == 0) rc_mbar_expect(mbar0 + 8 * (it & 1), (unsigned)by);
+        }
+        // the next rows of my chains' windows; the per-chain test constants
+#pragma unroll
+        for (int cl = 0; cl < RC_CPC; cl++) {
+            const int c = bx * RC_CPC + cl, lo2 = s_old[c], nrow = wldp[c] - lo2;
+            if (nrow <= 0) continue;
+            const int32_t *src = Q.rsg + (size_t)(coff_s[c] + lo2 - cmin_s[c]) * 64;
+            for (int i = tid; i < nrow * 16; i += RC_THREADS) rc_cp16(&rsw[cl][(lo2 + (i >> 4)) & (RC_WN - 1)][(i & 15) * 4], src + i * 4);
+            if (tid < nrow) rc_cp4(&cevw[cl][(lo2 + tid) & (RC_WN - 1)], P.cev + off[c] + lo2 - cmin_s[c] + tid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (tid < RC_CPC * 64) {                                // {threshold (+1 on the chain's own column: its self-parent), span}
+            const int cl = tid >> 6, m = tid & 63;
+            cst[cl][m] = make_int2(wp[m] + (m == bx * RC_CPC + cl ? 1 : 0), cnts[m]);
+        }
+        const long long t1 = clock64();
+        // ---- a: the masks of my members' ranges into my own table (4 warps per member), then each member's masks to
+        //         every other CTA as one wide store per (member, CTA).  Bit b of a mask's low word is column 2b, of its
+        //         high word column 2b+1: the tests only COUNT columns.
+        {
+            const int cl = warp / RC_WPC, c = bx * RC_CPC + cl, lo = slo[c], cnt = cnts[c];
+            const int2 wv = reinterpret_cast<const int2 *>(wp)[lane];
+            for (int i = warp % RC_WPC; i < cnt; i += RC_WPC) {
+                const int2 v = reinterpret_cast<const int2 *>(rsw[cl][(lo + i) & (RC_WN - 1)])[lane];
+                const unsigned b0 = __ballot_sync(0xffffffffu, v.x >= wv.x), b1 = __ballot_sync(0xffffffffu, v.y >= wv.y);
+                if (lane == 0) maskbuf[c][i] = (u64)b0 | (u64)b1 << 32;
             }
             __syncthreads();
             for (int pair = warp; pair < RC_CPC * RC_CS; pair += RC_THREADS / 32) {
-                const int cl = pair & (RC_CPC - 1), r = pair / RC_CPC, c = bx * RC_CPC + cl;
-                if (r == bx || 2 * lane >= cnt[cl]) continue;
-                const uint4 val = *reinterpret_cast<const uint4 *>(&maskbuf[c][2 * lane]);
-                rc_st_v4(rc_map(&maskbuf[c][2 * lane], (unsigned)r), val);
+                const int cl2 = pair & (RC_CPC - 1), r = pair / RC_CPC, c2 = bx * RC_CPC + cl2;
+                if (r == bx || 2 * lane >= cnts[c2]) continue;
+                const uint4 val = *reinterpret_cast<const uint4 *>(&maskbuf[c2][2 * lane]);
+                if (MB) rc_sta_v4(rc_map(&maskbuf[c2][2 * lane], (unsigned)r), val, rc_map(iv + 2304 + 2 * (it & 1), (unsigned)r));
+                else rc_st_v4(rc_map(&maskbuf[c2][2 * lane], (unsigned)r), val);
             }
         }
         const long long t2 = clock64();
-        rc_cluster_sync();
-        const long long t3 = clock64();
+        if (!MB) rc_cluster_arrive();
+        long long t3;
         // ---- b: first pending event with P_r (1) or beyond the masks (2), per chain
         if (UNIT) {
             // every position of the window at once, bit-sliced: 8 tests per warp, 4 lanes x 16 members per test.  A lane
             // adds the masks of its live members into a vertical counter (one bit plane per power of two, 64 columns
             // wide), the 4 lanes of a test add their counters, and the column counts are compared with the threshold
-            // plane by plane -- no transposes, ~50 instructions per test.
+            // plane by plane -- no transposes.  What needs only MY rows runs before the wait for the others' masks.
             const int cl = warp / RC_WPC, c = bx * RC_CPC + cl;
             const int q = lane >> 2, pp = lane & 3, t = (warp % RC_WPC) * 8 + q;
-            const int win = swin[c];
-            const bool act = t < win;
+            const bool act = t < swin[c];
             const int thr_i = (int)thr;
-            int v = 0;
-            if (__any_sync(0xffffffffu, act)) {
+            const int sq = spos[c] + t;
+            const char *rowb = reinterpret_cast<const char *>(rsw[cl][sq & (RC_WN - 1)]) + 64 * pp;
+            const char *cstb = reinterpret_cast<const char *>(cst[cl]) + 128 * pp;
+            const int r4 = (2 * q + (pp >> 1)) * 4;            // (the 32 lanes start at 32 different banks)
+            int offs[16], neg = 0;
+            bool unk = false;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int bo = (4 * i + r4) & 60;               // member 16 pp + bo / 4
+                const int pr = *reinterpret_cast<const int *>(rowb + bo);
+                const int2 cs = *reinterpret_cast<const int2 *>(cstb + 2 * bo);
+                const int o2 = act ? pr - cs.x : -1;            // >= 0: the member is live, its mask is maskbuf[m][o2]
+                unk |= o2 >= cs.y;                             // ... unless the event lies beyond the prepared masks
+                neg += o2 >> 31;
+                offs[i] = max(o2, -1);
+            }
+            int lv = 16 + neg;
+            lv += __shfl_xor_sync(0xffffffffu, lv, 1);
+            lv += __shfl_xor_sync(0xffffffffu, lv, 2);
+            const unsigned ub = __ballot_sync(0xffffffffu, unk);
+            unk = ((ub >> (lane & ~3)) & 0xfu) != 0;
+            const bool need = act && lv > thr_i && !unk;       // (lv <= thr: hits[c_] <= the live members)
+            int v = (act && lv > thr_i && unk) ? 2 : 0;
+            if (MB) late = !rc_mbar_wait(mbar0 + 8 * (it & 1), (it >> 1) & 1);
+            else rc_cluster_wait();
+            t3 = clock64();
+            if (__any_sync(0xffffffffu, need)) {
                 c_tests++;
-                const int sq = cmin_s[c] + pos[c] + t;
-                const int *row = rsw[cl][sq & (RC_WN - 1)];
-                const int rot = 2 * q + (pp >> 1);             // (the 32 lanes read 32 different banks)
-                int offs[16];
-                int lv = 0;
-                bool unk = false;
+                u64 x[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const int m = 16 * pp + ((i + rot) & 15);
-                    const int pr = act ? (m == c ? sq - 1 : row[m]) : -1;   // the own column is set back to the self-parent
-                    const int W = slo[m];
-                    const bool live = act && W >= 0 && pr >= W;
-                    if (live && pr >= smend[m]) unk = true;
-                    offs[i] = live ? pr - W : -1;
-                    lv += live ? 1 : 0;
+                    const int m = 16 * pp + (((4 * i + r4) & 60) >> 2);
+                    x[i] = (need && offs[i] >= 0) ? maskbuf[m][offs[i]] : 0ull;
                 }
-                lv += __shfl_xor_sync(0xffffffffu, lv, 1);
-                lv += __shfl_xor_sync(0xffffffffu, lv, 2);
-                const unsigned ub = __ballot_sync(0xffffffffu, unk);
-                unk = ((ub >> (lane & ~3)) & 0xfu) != 0;
-                const bool need = act && lv > thr_i && !unk;   // (lv <= thr: hits[c_] <= the live members)
-                if (act && lv > thr_i && unk) { v = 2; c_unk++; }
-                if (__any_sync(0xffffffffu, need)) {
-                    u64 x[16];
+                u64 a[8], t2a, t2b, t4a, t4b, t8a, t8b;
+                a[0] = a[1] = a[2] = a[3] = 0;
+                rc_csa(t2a, a[0], a[0], x[0], x[1]);   rc_csa(t2b, a[0], a[0], x[2], x[3]);   rc_csa(t4a, a[1], a[1], t2a, t2b);
+                rc_csa(t2a, a[0], a[0], x[4], x[5]);   rc_csa(t2b, a[0], a[0], x[6], x[7]);   rc_csa(t4b, a[1], a[1], t2a, t2b);
+                rc_csa(t8a, a[2], a[2], t4a, t4b);
+                rc_csa(t2a, a[0], a[0], x[8], x[9]);   rc_csa(t2b, a[0], a[0], x[10], x[11]); rc_csa(t4a, a[1], a[1], t2a, t2b);
+                rc_csa(t2a, a[0], a[0], x[12], x[13]); rc_csa(t2b, a[0], a[0], x[14], x[15]); rc_csa(t4b, a[1], a[1], t2a, t2b);
+                rc_csa(t8b, a[2], a[2], t4a, t4b);
+                rc_csa(a[4], a[3], a[3], t8a, t8b);           // 16 a[4] + 8 a[3] + 4 a[2] + 2 a[1] + a[0] = members per column
+                rc_vadd_xor<5>(a, 1);
+                rc_vadd_xor<6>(a, 2);                          // 7 planes: 0..64 per column
+                u64 gt = 0, eq = ~0ull;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int m = 16 * pp + ((i + rot) & 15);
-                        x[i] = (need && offs[i] >= 0) ? maskbuf[m][offs[i]] : 0ull;
-                    }
-                    u64 a[8], t2a, t2b, t4a, t4b, t8a, t8b;
-                    a[0] = a[1] = a[2] = a[3] = 0;
-                    rc_csa(t2a, a[0], a[0], x[0], x[1]);   rc_csa(t2b, a[0], a[0], x[2], x[3]);   rc_csa(t4a, a[1], a[1], t2a, t2b);
-                    rc_csa(t2a, a[0], a[0], x[4], x[5]);   rc_csa(t2b, a[0], a[0], x[6], x[7]);   rc_csa(t4b, a[1], a[1], t2a, t2b);
-                    rc_csa(t8a, a[2], a[2], t4a, t4b);
-                    rc_csa(t2a, a[0], a[0], x[8], x[9]);   rc_csa(t2b, a[0], a[0], x[10], x[11]); rc_csa(t4a, a[1], a[1], t2a, t2b);
-                    rc_csa(t2a, a[0], a[0], x[12], x[13]); rc_csa(t2b, a[0], a[0], x[14], x[15]); rc_csa(t4b, a[1], a[1], t2a, t2b);
-                    rc_csa(t8b, a[2], a[2], t4a, t4b);
-                    rc_csa(a[4], a[3], a[3], t8a, t8b);       // 16 a[4] + 8 a[3] + 4 a[2] + 2 a[1] + a[0] = members per column
-                    rc_vadd_xor<5>(a, 1);
-                    rc_vadd_xor<6>(a, 2);                      // 7 planes: 0..64 per column
-                    u64 gt = 0, eq = ~0ull;
-#pragma unroll
-                    for (int k = 6; k >= 0; k--) {
-                        const u64 tk = ((thr_i >> k) & 1) ? ~0ull : 0ull;
-                        gt |= eq & a[k] & ~tk;
-                        eq &= ~(a[k] ^ tk);
-                    }
-                    if (need) v = __popcll(gt) > thr_i ? 1 : 0; // a COUNT of members against the STAKE threshold (quirk Q3)
+                for (int k = 6; k >= 0; k--) {
+                    const u64 tk = ((thr_i >> k) & 1) ? ~0ull : 0ull;
+                    gt |= eq & a[k] & ~tk;
+                    eq &= ~(a[k] ^ tk);
                 }
+                if (need) v = __popcll(gt) > thr_i ? 1 : 0;    // a COUNT of members against the STAKE threshold (quirk Q3)
             }
-            if (pp == 0) vres[cl * RC_LW + t] = act ? v : 0;
-            __syncthreads();
+            if (v == 2) c_unk++;
+            if (pp == 0) vres[cl * RC_LW + t] = v;
+            if (__syncthreads_or(late)) {
+                if (tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -4);
+                handed = 1;
+                break;
+            }
             if (warp < RC_CPC) {
-                const int w2 = swin[bx * RC_CPC + warp];
+                const int c2 = bx * RC_CPC + warp, w2 = swin[c2];
                 const int x = vres[warp * RC_LW + lane];
                 const unsigned inwin = w2 >= 32 ? 0xffffffffu : (w2 > 0 ? (1u << w2) - 1u : 0u);
                 const unsigned nz = __ballot_sync(0xffffffffu, x != 0) & inwin;
                 const int f = nz ? __ffs(nz) - 1 : max(w2, 0);
-                const int vf = __shfl_sync(0xffffffffu, x, f & 31);
-                if (lane == 0) { sb[warp] = f; svb[warp] = nz ? vf : 0; }
+                const int vf = nz ? __shfl_sync(0xffffffffu, x, f & 31) : 0;
+                if (lane < RC_CS) {
+                    const unsigned xv = w2 >= 0 ? (unsigned)(f << 2 | vf) : 0u;
+                    if (MB) rc_sta_u32(rc_map(&xres[c2], (unsigned)lane), xv, rc_map(iv + 2304 + 4, (unsigned)lane));
+                    else rc_st_u32(rc_map(&xres[c2], (unsigned)lane), xv);
+                }
             }
-            __syncthreads();
         } else {
+            if (MB) late = !rc_mbar_wait(mbar0 + 8 * (it & 1), (it >> 1) & 1);
+            else rc_cluster_wait();
+            if (__syncthreads_or(late)) {
+                if (tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -4);
+                handed = 1;
+                break;
+            }
+            t3 = clock64();
             // integer stakes: a 5-ary search with the chain's 4 warps, one test of swirld_rounds.cuh's kind per warp and pass
             if (tid < RC_CPC) { sa[tid] = -1; sb[tid] = max(swin[bx * RC_CPC + tid], 0); svb[tid] = 0; }
             __syncthreads();
@@ -353,53 +472,47 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
                     else t = a + ((i + 1) * (nun + 1)) / (RC_WPC + 1);
                 }
                 int v = 0;
-                if (t >= 0) {                                       // (warp-uniform)
+                if (t >= 0) {                                   // (warp-uniform)
                     c_tests++;
-                    const int sq = cmin_s[c] + pos[c] + t;
+                    const int sq = spos[c] + t;
                     const int *row = rsw[cl][sq & (RC_WN - 1)];
                     int pre[2], W[2];
                     bool live[2];
                     i64 lv = 0;
-    #pragma unroll
+#pragma unroll
                     for (int j = 0; j < 2; j++) {
                         const int m = lane + 32 * j;
-                        pre[j] = m == c ? sq - 1 : row[m];          // the own column is set back to the self-parent
+                        pre[j] = m == c ? sq - 1 : row[m];      // the own column is set back to the self-parent
                         W[j] = slo[m];
                         live[j] = W[j] >= 0 && pre[j] >= W[j];
-                        if (UNIT) lv += __popc(__ballot_sync(0xffffffffu, live[j]));
-                        else {
-                            i64 s = live[j] ? stake_s[m] : 0;
-    #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                            lv += s;
-                        }
+                        i64 sv = live[j] ? stake_s[m] : 0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                        lv += sv;
                     }
-                    if (lv > thr) {                                 // else: hits[c_] <= stake of the live members
+                    if (lv > thr) {                             // else: hits[c_] <= stake of the live members
                         const bool unk = (live[0] && pre[0] >= smend[lane]) || (live[1] && pre[1] >= smend[lane + 32]);
                         if (__any_sync(0xffffffffu, unk)) { v = 2; c_unk++; }
                         else {
                             u64 mm[2];
-    #pragma unroll
+#pragma unroll
                             for (int j = 0; j < 2; j++) mm[j] = live[j] ? maskbuf[lane + 32 * j][pre[j] - W[j]] : 0ull;
-                            unsigned T[2][2];                       // T[jj][j]: bit b = member jj*32+b sees column j*32+lane
-    #pragma unroll
+                            unsigned T[2][2];                   // T[jj][j]: bit b = member jj*32+b sees the column of bit (j, lane)
+#pragma unroll
                             for (int jj = 0; jj < 2; jj++)
-    #pragma unroll
+#pragma unroll
                                 for (int j = 0; j < 2; j++) T[jj][j] = rb_transpose32((unsigned)(mm[jj] >> (32 * j)), lane);
                             int cntc = 0;
-    #pragma unroll
+#pragma unroll
                             for (int j = 0; j < 2; j++) {
                                 i64 hits = 0;
-                                if (UNIT) hits = __popc(T[0][j]) + __popc(T[1][j]);
-                                else {
-    #pragma unroll
-                                    for (int jj = 0; jj < 2; jj++)
-    #pragma unroll 8
-                                        for (int bq = 0; bq < 32; bq++) hits += ((T[jj][j] >> bq) & 1) ? stake_s[jj * 32 + bq] : 0;
-                                }
+#pragma unroll
+                                for (int jj = 0; jj < 2; jj++)
+#pragma unroll 8
+                                    for (int bq = 0; bq < 32; bq++) hits += ((T[jj][j] >> bq) & 1) ? stake_s[jj * 32 + bq] : 0;
                                 cntc += __popc(__ballot_sync(0xffffffffu, hits > thr));
                             }
-                            v = (i64)cntc > thr ? 1 : 0;           // a COUNT of members against the STAKE threshold (quirk Q3)
+                            v = (i64)cntc > thr ? 1 : 0;       // a COUNT of members against the STAKE threshold (quirk Q3)
                         }
                     }
                 }
@@ -407,7 +520,7 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
                 __syncthreads();
                 if (tid < RC_CPC) {
                     int a2 = sa[tid], b2 = sb[tid], vb2 = svb[tid];
-    #pragma unroll
+#pragma unroll
                     for (int q = 0; q < RC_WPC; q++) {
                         const int x = tres[tid * RC_WPC + q];
                         if (x < 0) continue;
@@ -419,86 +532,25 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
                 }
                 __syncthreads();
             }
+            if (tid < RC_CPC * RC_CS) {                         // (first position, what it is) of my chains to every CTA
+                const int cl = tid & (RC_CPC - 1), rank = tid / RC_CPC, c = bx * RC_CPC + cl;
+                unsigned x = 0;
+                if (swin[c] >= 0) { const int f = sb[cl]; x = (unsigned)(f << 2 | (f < swin[c] ? svb[cl] : 0)); }
+                if (MB) rc_sta_u32(rc_map(&xres[c], (unsigned)rank), x, rc_map(iv + 2304 + 4, (unsigned)rank));
+                else rc_st_u32(rc_map(&xres[c], (unsigned)rank), x);
+            }
         }
         const long long t4 = clock64();
-        // ---- c: (first position, what it is) of my chains to every CTA
-        if (tid < RC_CPC * RC_CS) {
-            const int cl = tid & (RC_CPC - 1), rank = tid / RC_CPC, c = bx * RC_CPC + cl;
-            unsigned x = 0;
-            if (swin[c] >= 0) { const int f = sb[cl]; x = (unsigned)(f << 2 | (f < swin[c] ? svb[cl] : 0)); }
-            rc_st_u32(rc_map(&xres[c], (unsigned)rank), x);
-        }
-        rc_cluster_sync();
+        if (!MB) rc_cluster_sync();
         const long long t5 = clock64();
-        // ---- d: identical bookkeeping in every CTA
-        bool tested = false;
-        int f = 0, vf = 0;
-        if (tid < 64 && swin[tid] >= 0) { tested = true; const int x = xres[tid]; f = x >> 2; vf = x & 3; }
-        if (__syncthreads_or(tested && vf == 1 && rmin + 1 > rtop)) {       // open the mirror row of round rmin+1
-            rtop = rmin + 1;
-            if (tid < 64) Wls[rtop & (RB_WR - 1)][tid] = -1;
-            if (rtop >= P.Rcap && tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -5);
-            __syncthreads();
-        }
-        if (tid < 64) {
-            const int c = tid;
-            int nf = 0, base = 0;
-            if (tested) {
-                const int op = pos[c];
-                base = cmin_s[c] + op; nf = f;
-                if (vf == 1) {
-                    cur[c] = rmin + 1;
-                    if (rmin + 1 < P.Rcap) {
-                        Wls[(rmin + 1) & (RB_WR - 1)][c] = cmin_s[c] + op + f;
-                        if (c / RC_CPC == bx) P.Wf[(size_t)(rmin + 1) * M + c] = cevw[c % RC_CPC][(cmin_s[c] + op + f) & (RC_WN - 1)];
-                    }
-                }
-                pos[c] = op + f;
-            }
-            s_nfin[c] = nf; s_base[c] = base;
-        }
-        const bool prog = __syncthreads_or(tested && (f > 0 || vf == 1));
-        if (tid < RC_CPC * RC_LW) {                             // final rounds of my chains' events before the first hit
-            const int cl = tid / RC_LW, j = tid % RC_LW, c = bx * RC_CPC + cl;
-            if (j < s_nfin[c]) P.round[cevw[cl][(s_base[c] + j) & (RC_WN - 1)]] = rmin;
-        }
-        // ---- the windows: what was issued a step ago has arrived; issue the next rows
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        const int rnext = lowest_open();
-        bool moved = false;
-        if (tid < 64) {
-            const int c = tid, sp = seqpos(c);
-            moved = wrd[c] != wld[c];
-            wrd[c] = wld[c];
-            if (rnext != RC_INF && rnext > rtop - RB_WR) {
-                const int l2 = Wls[rnext & (RB_WR - 1)][c];
-                wlo[c] = max(wlo[c], l2 >= 0 ? min(l2, sp) : sp);
-            }
-            const int hi = min(min(ctot_s[c], wlo[c] + RC_WN), sp + RC_LW + RC_PF);
-            s_old[c] = wld[c];
-            if (hi > wld[c]) { wld[c] = hi; moved = true; }
-        }
-        const bool mv = __syncthreads_or(moved);                // (also: the arrived rows are visible to all warps)
-#pragma unroll
-        for (int cl = 0; cl < RC_CPC; cl++) {
-            const int c = bx * RC_CPC + cl, lo2 = s_old[c], nrow = wld[c] - lo2;
-            for (int i = tid; i < nrow * 16; i += RC_THREADS) {
-                const int sq = lo2 + (i >> 4), q = i & 15;
-                rc_cp16(&rsw[cl][sq & (RC_WN - 1)][q * 4], Q.rsg + (size_t)(coff_s[c] + sq - cmin_s[c]) * 64 + q * 4);
-                if (q == 0) rc_cp4(&cevw[cl][sq & (RC_WN - 1)], P.cev + off[c] + sq - cmin_s[c]);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        stall = (prog || mv) ? 0 : stall + 1;
-        if (stall >= RC_STALL) handed = 1;
-        const long long t6 = clock64();
-        c_t[0] += t1 - t0; c_t[1] += t2 - t1; c_t[2] += t3 - t2; c_t[3] += t4 - t3; c_t[4] += t5 - t4; c_t[5] += t6 - t5;
+        have_res = true;
+        c_t[0] += t1 - t0; c_t[1] += t2 - t1; c_t[2] += t3 - t2; c_t[3] += t4 - t3; c_t[4] += t5 - t4;
         c_steps++;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (lead) {
-        if (tid < 64) { Q.cont[tid] = pos[tid]; Q.cont[64 + tid] = cur[tid]; }
+        if (tid < 64) { Q.cont[tid] = my_pos; Q.cont[64 + tid] = my_cur; }
         if (tid == 0) {
             Q.cont[128] = handed;
             if (P.n > 0) P.scal[SC_MAX_ROUND] = rtop;
@@ -518,15 +570,15 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     rc_cluster_sync();                                          // nobody leaves while its shared memory may still be written
 }
 
-template <bool UNIT>
-__global__ void __launch_bounds__(RC_THREADS, 1) k_rounds_cluster(RcParams Q) { rounds_cluster_body<UNIT>(Q); }
+template <bool UNIT, bool MB>
+__global__ void __launch_bounds__(RC_THREADS, 1) k_rounds_cluster(RcParams Q) { rounds_cluster_body<UNIT, MB>(Q); }
 
 // several independent node-views (swirld_rounds.cuh, k_rounds_batch_views): one cluster per view, as many side by side
 // as the device holds -- the clusters never talk to each other, so this is an ordinary (non-cooperative) launch
-template <bool UNIT>
+template <bool UNIT, bool MB>
 __global__ void __launch_bounds__(RC_THREADS, 1) k_rounds_cluster_views(const RcParams *Qv) {
     __shared__ RcParams Qs;
     if (threadIdx.x == 0) Qs = Qv[blockIdx.x / RC_CS];
     __syncthreads();
-    rounds_cluster_body<UNIT>(Qs);
+    rounds_cluster_body<UNIT, MB>(Qs);
 }

@@ -4,8 +4,9 @@ swirld_rounds.cuh with everything a step needs held inside ONE thread-block clus
   * rows in SEQ space (rs[h][c] = chain position of the event of member c that h sees), a sliding window of WN rows
     per chain in the shared memory of the CTA that owns the chain, loaded one step ahead;
   * per step the masks S_r of the members' ranges [Wls_r[m], mend[m]) (at most MR per member), pushed to every CTA;
-  * the first pending event of a chain that passes P_r found by a (WPC+1)-ary search over the window -- P_r and
-    "an event the masks do not cover" are both monotone along a chain;
+  * the first pending event of a chain that passes P_r, or that the masks do not cover: both are monotone along a
+    chain, so the kernel may test every position of the window (unit stake, bit-sliced) or search it (WPC+1)-ary
+    (integer stakes) -- the model searches, and asserts that the search closes;
   * anything the windows cannot decide (no progress for STALL steps, a round outside the mirror, an event beyond the
     ring) hands the rest of the chunk to the grid-wide kernel (modelled by RoundBatch with a start state).
 
