@@ -42,6 +42,7 @@
 #define RC_LW 32            // pending events searched per chain and step
 #define RC_WN 128           // rows per chain in shared memory (power of two)
 #define RC_MR 64            // masks per member and step
+#define RC_MRS 66           // ... and the stride of a member's masks in the table: rows 4 banks apart, 16-byte aligned
 #define RC_PF 32            // rows loaded beyond the searched window
 #define RC_PASSES 3         // (RC_WPC + 1) ^ RC_PASSES >= RC_LW + 1
 #define RC_STALL 3
@@ -56,7 +57,7 @@ struct RcParams {
 };
 
 #define RC_SMEM_ROWS ((size_t)RC_CPC * RC_WN * 64 * 4)
-#define RC_SMEM_MASK ((size_t)2 * 64 * RC_MR * 8)   // two mask tables: a CTA may receive the next step's masks while it still tests
+#define RC_SMEM_MASK ((size_t)2 * 64 * RC_MRS * 8)   // two mask tables: a CTA may receive the next step's masks while it still tests
 #define RC_SMEM_WLS ((size_t)RB_WR * 64 * 4)
 #define RC_SMEM_BYTES (RC_SMEM_ROWS + RC_SMEM_MASK + RC_SMEM_WLS + 512 + 10240)
 
@@ -145,7 +146,7 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     const RbParams &P = Q.R;
     extern __shared__ __align__(16) unsigned char rc_smem[];
     int (*rsw)[RC_WN][64] = reinterpret_cast<int (*)[RC_WN][64]>(rc_smem);                       // [chain][slot][member]
-    u64 (*maskbuf0)[RC_MR] = reinterpret_cast<u64 (*)[RC_MR]>(rc_smem + RC_SMEM_ROWS);           // [2][member][offset]
+    u64 (*maskbuf0)[RC_MRS] = reinterpret_cast<u64 (*)[RC_MRS]>(rc_smem + RC_SMEM_ROWS);           // [2][member][offset]
     int (*Wls)[64] = reinterpret_cast<int (*)[64]>(rc_smem + RC_SMEM_ROWS + RC_SMEM_MASK);       // seq of Wf_r[c], -1: none
     i64 *stake_s = reinterpret_cast<i64 *>(rc_smem + RC_SMEM_ROWS + RC_SMEM_MASK + RC_SMEM_WLS);
     int *iv = reinterpret_cast<int *>(stake_s + 64);
@@ -251,7 +252,7 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     unsigned it = 0;                                            // steps so far (mbarrier phases)
     for (; !handed; ++it) {
         const long long t0 = clock64();
-        u64 (*maskbuf)[RC_MR] = maskbuf0 + (MB ? (it & 1) * 64 : 0);
+        u64 (*maskbuf)[RC_MRS] = maskbuf0 + (MB ? (it & 1) * 64 : 0);
         // ---- the results of the last step (every CTA holds all of them): positions, rounds, the mirror of Wf
         bool late = false;
         if (MB) {
@@ -350,10 +351,21 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
         {
             const int cl = warp / RC_WPC, c = bx * RC_CPC + cl, lo = slo[c], cnt = cnts[c];
             const int2 wv = reinterpret_cast<const int2 *>(wp)[lane];
-            for (int i = warp % RC_WPC; i < cnt; i += RC_WPC) {
-                const int2 v = reinterpret_cast<const int2 *>(rsw[cl][(lo + i) & (RC_WN - 1)])[lane];
-                const unsigned b0 = __ballot_sync(0xffffffffu, v.x >= wv.x), b1 = __ballot_sync(0xffffffffu, v.y >= wv.y);
-                if (lane == 0) maskbuf[c][i] = (u64)b0 | (u64)b1 << 32;
+            for (int i0 = warp % RC_WPC; i0 < cnt; i0 += 4 * RC_WPC) {      // four rows in flight
+                int2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * RC_WPC;
+                    v[u] = i < cnt ? reinterpret_cast<const int2 *>(rsw[cl][(lo + i) & (RC_WN - 1)])[lane] : make_int2(-1, -1);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * RC_WPC;
+                    if (i < cnt) {                              // (warp-uniform)
+                        const unsigned b0 = __ballot_sync(0xffffffffu, v[u].x >= wv.x), b1 = __ballot_sync(0xffffffffu, v[u].y >= wv.y);
+                        if (lane == 0) maskbuf[c][i] = (u64)b0 | (u64)b1 << 32;
+                    }
+                }
             }
             __syncthreads();
             for (int pair = warp; pair < RC_CPC * RC_CS; pair += RC_THREADS / 32) {
