@@ -20,8 +20,8 @@ starting from an engine whose consensus state was cleared.  Workloads (BASELINE.
             reads back round / witness / famous for all events (D2H inside the timed region).
 `parity`  : the engine's round / witness / famous (c1-c3: of the whole trace; c4-c5: of a prefix run with the prefix
             as one chunk) compared element-wise with the oracle's, in this run.  A mismatch exits non-zero.
-`roofline`: the dominant kernel of the step (M <= 64: k_rounds_batch; above: k_rounds_wide or the can_see scan,
-            whichever takes longer) -- algorithmic bytes per event over its mean launch
+`roofline`: the dominant kernel of the step (M <= 64: the round kernel -- k_rounds_cluster for chunks of >= 2048
+            events, k_rounds_batch below; above 64 members: k_rounds_wide or the can_see scan, whichever takes longer) -- algorithmic bytes per event over its mean launch
             duration (CUDA events on the engine's stream) against MEASURED_PEAKS.json hbm_gbs.
 `roofline_can_see`: the same for the can_see kernel family k_cs_* (B1(M) = 12M + 12 bytes per event).
 `cpu_baseline` / --impl reference: the literal C restatement oracle/ (kind "port"), single-threaded per node-view
@@ -64,7 +64,8 @@ GEN_TEXT = {"gossip": "G1 reference-sim gossip", "gossip_np": "G1 reference-sim 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at c3 (65536 events), from the
 # committed ncu --set full capture (profiles/README.md); None where no capture of that launch shape exists
-DRAM_BYTES_PER_LAUNCH = {("k_rounds_batch", 64, 65536): 18547712 + 2816}
+DRAM_BYTES_PER_LAUNCH = {("k_rounds_batch", 64, 65536): 18547712 + 2816,
+                         ("k_rounds_cluster", 64, 65536): None}
 
 
 def algorithmic_bytes_per_event(M):
@@ -544,7 +545,9 @@ def bench_ours(args, wl, rank, world, local_rank):
         ms_cs = st1["ms_can_see"] - st0["ms_can_see"]
         ms_rk = st1["ms_rounds_kernel"] - st0["ms_rounds_kernel"]
         wide = M > 64 or os.environ.get("SW_FORCE_WIDE", "0") not in ("", "0")
-        rk_name = "k_rounds_wide" if wide else "k_rounds_batch"
+        cluster = (not wide and K >= int(os.environ.get("SW_RC_MIN_N", "2048"))
+                   and os.environ.get("SW_ROUNDS_CLUSTER", "1") not in ("", "0"))
+        rk_name = "k_rounds_wide" if wide else ("k_rounds_cluster" if cluster else "k_rounds_batch")
         dominant_cs = ms_cs > ms_rk
         cs_achieved = (N * args.steps * can_see_bytes_per_event(M)) / (ms_cs * 1e-3) / 1e9 if ms_cs > 0 else None
         rk_achieved = (N * args.steps * rounds_bytes_per_event(M)) / (ms_rk * 1e-3) / 1e9 if ms_rk > 0 else None
@@ -616,8 +619,11 @@ def bench_ours(args, wl, rank, world, local_rank):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_event": dom_bpe, "events_per_launch": K,
                          "ms_per_launch": dom_ms / n_div_launch,
-                         "note": "latency-bound, not HBM-bound: the depth of the computation is the number of rounds (one "
-                                 "grid-wide step per round at M <= 64, a few steps per round above); DESIGN.md section 5"},
+                         "note": "latency-bound, not HBM-bound: the depth of the computation is the number of rounds (one step "
+                                 "per round at M <= 64 -- inside one thread-block cluster for chunks >= 2048 events, "
+                                 "grid-wide below --, a few grid-wide steps per round above 64 members); ms_per_launch "
+                                 "covers the round kernel(s) of one divide_rounds call (k_rc_seqrows + k_rounds_cluster "
+                                 "+ the hand-over launch of k_rounds_batch); DESIGN.md section 5"},
             "roofline_can_see": None if cs_achieved is None else {
                 "bound": "hbm", "kernel": "k_cs_prep + k_cs_pass<1> + k_cs_heads + k_cs_check + k_cs_slow + k_cs_pass<2> "
                                           "(column-tiled blocked max-plus scan)",

@@ -175,9 +175,8 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
         const int w = (c < M && r >= 0 && r < P.Rcap) ? __ldcg(P.Wf + (size_t)r * M + c) : -1;
         Wls[slot][c] = w >= 0 ? P.seq[w] : -1;
     }
-    // ---- the state of chain c lives in the registers of thread c
-    int my_pos = 0, my_cur = RC_INF, my_len = 0, my_cmin = 0, my_ctot = 0, my_wlo = 0, my_wld = 0, my_wrd = 0;
-    bool my_tested = false;
+    // ---- the launch-time state of chain c, by thread c
+    int my_cur = RC_INF, my_len = 0, my_cmin = 0, my_ctot = 0, my_wlo = 0, my_wld = 0, my_wrd = 0;
     if (tid < 64) {
         const int c = tid;
         stake_s[c] = c < M ? P.stake[c] : 0;
@@ -246,6 +245,19 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     }
     rc_cluster_sync();                                          // every CTA of the cluster runs before any remote store
 
+    // ---- from here on the state of chain c lives in the registers of ONE warp: lane l of warp 0 holds chains l and l+32
+    int cpos[2] = {0, 0}, ccur[2] = {RC_INF, RC_INF}, clen[2] = {0, 0}, ccmin[2] = {0, 0}, cctot[2] = {0, 0};
+    int cwlo[2] = {0, 0}, cwld[2] = {0, 0}, cwrd[2] = {0, 0};
+    bool ctested[2] = {false, false};
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int c = lane + 32 * j;
+            clen[j] = len_s[c]; ccmin[j] = cmin_s[c]; cctot[j] = ctot_s[c]; ccur[j] = cur0[c];
+            if (!handed) { cwlo[j] = s_old[c]; cwld[j] = cwrd[j] = wldp[c]; }
+        }
+    }
+
     long long c_t[6] = {0, 0, 0, 0, 0, 0}, c_steps = 0, c_tests = 0, c_unk = 0;
     int stall = 0, rmin = 0;
     bool have_res = false;
@@ -253,96 +265,91 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     for (; !handed; ++it) {
         const long long t0 = clock64();
         u64 (*maskbuf)[RC_MRS] = maskbuf0 + (MB ? (it & 1) * 64 : 0);
-        // ---- the results of the last step (every CTA holds all of them): positions, rounds, the mirror of Wf
+        // ---- the results of the last step (every CTA holds all of them): positions, rounds, the mirror of Wf; then
+        //      this step's ranges and windows.  One warp, no block-wide barrier inside.
         bool late = false;
         if (MB) {
             if (have_res) late = !rc_mbar_wait(mbar0 + 16, (it - 1) & 1);
             if (tid == 0) rc_mbar_expect(mbar0 + 16, 64 * 4);  // this step's results: one word per chain
         }
         asm volatile("cp.async.wait_all;" ::: "memory");        // (the rows issued a step ago)
-        int nf = 0, base = 0, hitseq = -1;
-        bool hit = false, prog = false;
-        if (tid < 64) {
-            if (have_res && my_tested) {
-                const int x = xres[tid], f = x >> 2, vf = x & 3;
-                base = my_cmin + my_pos; nf = f;
-                if (vf == 1) { hit = true; my_cur = rmin + 1; hitseq = base + f; }
-                my_pos += f;
-                prog = f > 0 || vf == 1;
+        if (warp == 0) {
+            bool hit[2] = {false, false}, prog = false;
+            int hitseq[2] = {-1, -1};
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int c = lane + 32 * j;
+                int nf = 0, base = 0;
+                if (have_res && ctested[j]) {
+                    const int x = xres[c], f = x >> 2, vf = x & 3;
+                    base = ccmin[j] + cpos[j]; nf = f;
+                    if (vf == 1) { hit[j] = true; ccur[j] = rmin + 1; hitseq[j] = base + f; }
+                    cpos[j] += f;
+                    prog |= f > 0 || vf == 1;
+                }
+                s_nfin[c] = nf; s_base[c] = base;
             }
-            s_nfin[tid] = nf; s_base[tid] = base;
+            const int rnext = __reduce_min_sync(0xffffffffu, min(cpos[0] < clen[0] ? ccur[0] : RC_INF, cpos[1] < clen[1] ? ccur[1] : RC_INF));
+            const bool anyhit = __any_sync(0xffffffffu, hit[0] || hit[1]), anyprog = __any_sync(0xffffffffu, prog);
+            bool newrow = false;
+            if (have_res && anyhit && rmin + 1 > rtop) {        // the hits open the mirror row of round rmin+1
+                rtop = rmin + 1; newrow = true;
+                if (rtop >= P.Rcap && lane == 0 && lead) atomicMin(&P.scal[SC_ERR], -5);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {                       // (each lane its own columns)
+                const int c = lane + 32 * j;
+                if (hit[j] && rmin + 1 < P.Rcap) {
+                    Wls[(rmin + 1) & (RB_WR - 1)][c] = hitseq[j];
+                    if (c / RC_CPC == bx) P.Wf[(size_t)(rmin + 1) * M + c] = cevw[c % RC_CPC][hitseq[j] & (RC_WN - 1)];
+                } else if (newrow) Wls[rtop & (RB_WR - 1)][c] = -1;
+            }
+            int status = 0;                                     // 1: every chain is done, 2: the rest goes to k_rounds_batch
+            if (rnext == RC_INF) status = 1;
+            else if (rnext <= rtop - RB_WR) status = 2;
+            else {
+                bool moved = false;
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int c = lane + 32 * j, sp = clen[j] > 0 ? ccmin[j] + cpos[j] : cctot[j];
+                    moved |= cwrd[j] != cwld[j];
+                    cwrd[j] = cwld[j];
+                    const int lo = Wls[rnext & (RB_WR - 1)][c];
+                    cwlo[j] = max(cwlo[j], lo >= 0 ? min(lo, sp) : sp);
+                    const int hi = min(min(cctot[j], cwlo[j] + RC_WN), sp + RC_LW + RC_PF), old = cwld[j];
+                    if (hi > cwld[j]) { cwld[j] = hi; moved = true; }
+                    const bool open = cpos[j] < clen[j];
+                    const int me = lo >= 0 ? min(min(cwrd[j], open ? sp + RC_LW : cctot[j]), lo + RC_MR) : -1;
+                    ctested[j] = open && ccur[j] == rnext;
+                    slo[c] = lo; smend[c] = me; spos[c] = sp; s_old[c] = old; wldp[c] = cwld[j];
+                    swin[c] = ctested[j] ? max(0, min(min(RC_LW, clen[j] - cpos[j]), cwrd[j] - sp)) : -1;
+                    cnts[c] = lo >= 0 ? max(0, me - lo) : 0;
+                    wp[c] = lo >= 0 ? lo : RC_BIG;
+                }
+                const bool anymoved = __any_sync(0xffffffffu, moved);
+                if (have_res) stall = (anyprog || anymoved) ? 0 : stall + 1;
+                if (stall >= RC_STALL) status = 2;
+                else if (MB) {                                  // the bytes the other CTAs will store into my mask table
+                    int by = 0;
+#pragma unroll
+                    for (int j = 0; j < 2; j++) { const int m = lane + 32 * j; if (m / RC_CPC != bx) by += ((cnts[m] + 1) >> 1) * 16; }
+                    by = __reduce_add_sync(0xffffffffu, by);
+                    if (lane == 0) rc_mbar_expect(mbar0 + 8 * (it & 1), (unsigned)by);
+                }
+            }
+            if (lane == 0) { ws[0] = rnext; ws[1] = status; }
         }
-        if (warp < 2) {
-            const int cm = __reduce_min_sync(0xffffffffu, my_pos < my_len ? my_cur : RC_INF);
-            const int fl = (__any_sync(0xffffffffu, hit) ? 1 : 0) | (__any_sync(0xffffffffu, prog) ? 2 : 0);
-            if (lane == 0) { ws[2 * warp] = cm; ws[2 * warp + 1] = fl; }
-        }
-        if (__syncthreads_or(late)) {                           // (never, unless a peer CTA died)
-            if (tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -4);
-            handed = 1;
+        const bool timed_out = __syncthreads_or(late);          // (never, unless a peer CTA died)
+        const int rprev = rmin, status = ws[1];
+        rmin = ws[0];
+        if (timed_out || status != 0) {
+            if (have_res && !timed_out && tid < RC_CPC * RC_LW) {   // final rounds of the last step
+                const int cl = tid / RC_LW, j = tid % RC_LW, c = bx * RC_CPC + cl;
+                if (j < s_nfin[c]) P.round[cevw[cl][(s_base[c] + j) & (RC_WN - 1)]] = rprev;
+            }
+            if (timed_out && tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -4);
+            if (timed_out || status == 2) handed = 1;
             break;
-        }
-        const int rnext = min(ws[0], ws[2]), fl = ws[1] | ws[3];  // lowest open round; any hit / any progress
-        bool newrow = false;
-        if (have_res && (fl & 1) && rmin + 1 > rtop) {          // the hits open the mirror row of round rmin+1
-            rtop = rmin + 1; newrow = true;
-            if (rtop >= P.Rcap && tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -5);
-        }
-        if (tid < 64) {                                         // (each thread its own column)
-            if (hit && rmin + 1 < P.Rcap) {
-                Wls[(rmin + 1) & (RB_WR - 1)][tid] = hitseq;
-                if (tid / RC_CPC == bx) P.Wf[(size_t)(rmin + 1) * M + tid] = cevw[tid % RC_CPC][hitseq & (RC_WN - 1)];
-            } else if (newrow) Wls[rtop & (RB_WR - 1)][tid] = -1;
-        }
-        if (have_res && tid < RC_CPC * RC_LW) {                 // final rounds of my chains' events before the first hit
-            const int cl = tid / RC_LW, j = tid % RC_LW, c = bx * RC_CPC + cl;
-            if (j < s_nfin[c]) P.round[cevw[cl][(s_base[c] + j) & (RC_WN - 1)]] = rmin;
-        }
-        if (rnext == RC_INF) break;                             // every chain is done
-        if (rnext <= rtop - RB_WR) { handed = 1; break; }
-        // ---- this step's ranges and windows
-        bool moved = false;
-        if (tid < 64) {
-            const int c = tid, sp = my_len > 0 ? my_cmin + my_pos : my_ctot;
-            moved = my_wrd != my_wld;
-            my_wrd = my_wld;
-            const int lo = Wls[rnext & (RB_WR - 1)][c];
-            my_wlo = max(my_wlo, lo >= 0 ? min(lo, sp) : sp);
-            const int hi = min(min(my_ctot, my_wlo + RC_WN), sp + RC_LW + RC_PF), old = my_wld;
-            if (hi > my_wld) { my_wld = hi; moved = true; }
-            const bool open = my_pos < my_len;
-            const int me = lo >= 0 ? min(min(my_wrd, open ? sp + RC_LW : my_ctot), lo + RC_MR) : -1;
-            my_tested = open && my_cur == rnext;
-            slo[c] = lo; smend[c] = me; spos[c] = sp; s_old[c] = old; wldp[c] = my_wld;
-            swin[c] = my_tested ? max(0, min(min(RC_LW, my_len - my_pos), my_wrd - sp)) : -1;
-            cnts[c] = lo >= 0 ? max(0, me - lo) : 0;
-            wp[c] = lo >= 0 ? lo : RC_BIG;
-        }
-        if (warp < 2) { const bool am = __any_sync(0xffffffffu, moved); if (lane == 0) ws[4 + warp] = am ? 1 : 0; }
-        __syncthreads();
-        if (have_res) stall = ((fl & 2) || ws[4] || ws[5]) ? 0 : stall + 1;
-        if (stall >= RC_STALL) { handed = 1; break; }
-        rmin = rnext;
-        if (MB && warp == 0) {                                  // the bytes the other CTAs will store into my mask table
-            int by = 0;
-#pragma unroll
-            for (int j = 0; j < 2; j++) { const int m = lane + 32 * j; if (m / RC_CPC != bx) by += ((cnts[m] + 1) >> 1) * 16; }
-            by = __reduce_add_sync(0xffffffffu, by);
-            if (lane == 0) rc_mbar_expect(mbar0 + 8 * (it & 1), (unsigned)by);
-        }
-        // the next rows of my chains' windows; the per-chain test constants
-#pragma unroll
-        for (int cl = 0; cl < RC_CPC; cl++) {
-            const int c = bx * RC_CPC + cl, lo2 = s_old[c], nrow = wldp[c] - lo2;
-            if (nrow <= 0) continue;
-            const int32_t *src = Q.rsg + (size_t)(coff_s[c] + lo2 - cmin_s[c]) * 64;
-            for (int i = tid; i < nrow * 16; i += RC_THREADS) rc_cp16(&rsw[cl][(lo2 + (i >> 4)) & (RC_WN - 1)][(i & 15) * 4], src + i * 4);
-            if (tid < nrow) rc_cp4(&cevw[cl][(lo2 + tid) & (RC_WN - 1)], P.cev + off[c] + lo2 - cmin_s[c] + tid);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (tid < RC_CPC * 64) {                                // {threshold (+1 on the chain's own column: its self-parent), span}
-            const int cl = tid >> 6, m = tid & 63;
-            cst[cl][m] = make_int2(wp[m] + (m == bx * RC_CPC + cl ? 1 : 0), cnts[m]);
         }
         const long long t1 = clock64();
         // ---- a: the masks of my members' ranges into my own table (4 warps per member), then each member's masks to
@@ -367,6 +374,10 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
                     }
                 }
             }
+            if (tid < RC_CPC * 64) {                            // {threshold (+1 on the chain's own column: its self-parent), span}
+                const int cl2 = tid >> 6, m = tid & 63;
+                cst[cl2][m] = make_int2(wp[m] + (m == bx * RC_CPC + cl2 ? 1 : 0), cnts[m]);
+            }
             __syncthreads();
             for (int pair = warp; pair < RC_CPC * RC_CS; pair += RC_THREADS / 32) {
                 const int cl2 = pair & (RC_CPC - 1), r = pair / RC_CPC, c2 = bx * RC_CPC + cl2;
@@ -378,6 +389,20 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
         }
         const long long t2 = clock64();
         if (!MB) rc_cluster_arrive();
+        // off the path the other CTAs wait on: the final rounds of the last step, the next rows of my chains' windows
+        if (have_res && tid < RC_CPC * RC_LW) {
+            const int cl = tid / RC_LW, j = tid % RC_LW, c = bx * RC_CPC + cl;
+            if (j < s_nfin[c]) P.round[cevw[cl][(s_base[c] + j) & (RC_WN - 1)]] = rprev;
+        }
+#pragma unroll
+        for (int cl = 0; cl < RC_CPC; cl++) {
+            const int c = bx * RC_CPC + cl, lo2 = s_old[c], nrow = wldp[c] - lo2;
+            if (nrow <= 0) continue;
+            const int32_t *src = Q.rsg + (size_t)(coff_s[c] + lo2 - cmin_s[c]) * 64;
+            for (int i = tid; i < nrow * 16; i += RC_THREADS) rc_cp16(&rsw[cl][(lo2 + (i >> 4)) & (RC_WN - 1)][(i & 15) * 4], src + i * 4);
+            if (tid < nrow) rc_cp4(&cevw[cl][(lo2 + tid) & (RC_WN - 1)], P.cev + off[c] + lo2 - cmin_s[c] + tid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         long long t3;
         // ---- b: first pending event with P_r (1) or beyond the masks (2), per chain
         if (UNIT) {
@@ -445,13 +470,14 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
             }
             if (v == 2) c_unk++;
             if (pp == 0) vres[cl * RC_LW + t] = v;
+            const int w2 = warp < RC_CPC ? swin[bx * RC_CPC + warp] : -1;   // (read before the barrier: warp 0 rewrites swin right after it)
             if (__syncthreads_or(late)) {
                 if (tid == 0 && lead) atomicMin(&P.scal[SC_ERR], -4);
                 handed = 1;
                 break;
             }
             if (warp < RC_CPC) {
-                const int c2 = bx * RC_CPC + warp, w2 = swin[c2];
+                const int c2 = bx * RC_CPC + warp;
                 const int x = vres[warp * RC_LW + lane];
                 const unsigned inwin = w2 >= 32 ? 0xffffffffu : (w2 > 0 ? (1u << w2) - 1u : 0u);
                 const unsigned nz = __ballot_sync(0xffffffffu, x != 0) & inwin;
@@ -562,7 +588,10 @@ __device__ __forceinline__ void rounds_cluster_body(const RcParams &Q) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (lead) {
-        if (tid < 64) { Q.cont[tid] = my_pos; Q.cont[64 + tid] = my_cur; }
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) { Q.cont[lane + 32 * j] = cpos[j]; Q.cont[64 + lane + 32 * j] = ccur[j]; }
+        }
         if (tid == 0) {
             Q.cont[128] = handed;
             if (P.n > 0) P.scal[SC_MAX_ROUND] = rtop;
