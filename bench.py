@@ -65,7 +65,7 @@ GEN_TEXT = {"gossip": "G1 reference-sim gossip", "gossip_np": "G1 reference-sim 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at c3 (65536 events), from the
 # committed ncu --set full capture (profiles/README.md); None where no capture of that launch shape exists
 DRAM_BYTES_PER_LAUNCH = {("k_rounds_batch", 64, 65536): 18547712 + 2816,
-                         ("k_rounds_cluster", 64, 65536): None}
+                         ("k_rounds_cluster", 64, 65536): 17356288 + 0}
 
 
 def algorithmic_bytes_per_event(M):
