@@ -52,7 +52,7 @@ typedef struct sw_stats_t {
     int64_t events;            /* events appended */
     int64_t events_divided;    /* events through divide_rounds */
     double ms_rounds_kernel;   /* subset of ms_divide_rounds spent in the round-number kernel itself
-                                  (k_rounds_batch; k_divide_levels with SW_DIVIDE_IMPL=4) */
+                                  (M <= 64: k_rc_seqrows + k_rounds_cluster + k_rounds_batch; above: k_rounds_wide) */
 } sw_stats_t;
 
 /* Node.__init__ state (swirld.py:38-72): M members, integer stake per member
@@ -89,8 +89,9 @@ int sw_divide_rounds(sw_engine *e, int first, int n);
 
 /* Node.divide_rounds for B independent node-views in one call (the simulation's M nodes each recompute consensus on
  * nearly the same graph, swirld.py:331-345 / viz.py:35-46): engines[v] divides its events [first[v], first[v]+n[v]).
- * M <= 64, same member count and stake shape, same device.  The views' round kernels advance side by side in ONE
- * cooperative launch (each on its own group of CTAs): the path is latency-bound, so this is what fills the GPU.
+ * M <= 64, same member count and stake shape, same device.  The views' round kernels advance side by side -- one
+ * thread-block cluster per view (chunks of >= 2048 events), then ONE cooperative launch, each view on its own group of
+ * CTAs, for what is left: the path is latency-bound, so this is what fills the GPU.
  * Results per view are identical to B separate sw_divide_rounds calls. */
 int sw_batch_divide_rounds(sw_engine *const *engines, int B, const int *first, const int *n);
 
@@ -128,7 +129,7 @@ int sw_flush_l2(sw_engine *e, int64_t bytes);
 int sw_event_record(sw_engine *e, int slot);
 int sw_event_elapsed_ms(sw_engine *e, int slot_a, int slot_b, double *ms_out);
 
-/* Profiling aid: 16 cycle counters of k_rounds_batch (tools/rounds_cycles.py). */
+/* Profiling aid: 16 cycle counters of the round kernels (tools/rounds_cycles.py). */
 int sw_debug_counters(sw_engine *e, int64_t *out16, int clear);
 
 /* ---- ingest: the step of Node.sync between the wire and divide_rounds (swirld.py:129-136, utils.py:8-21) in C++.
