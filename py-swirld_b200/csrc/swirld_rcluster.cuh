@@ -122,14 +122,15 @@ __device__ __forceinline__ void rc_mbar_init(unsigned mbar, unsigned count) { as
 __device__ __forceinline__ void rc_mbar_expect(unsigned mbar, unsigned bytes) {
     asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" :: "r"(mbar), "r"(bytes) : "memory");
 }
-// false: the bytes did not arrive within ~0.2 s (a bug or a dead peer CTA; the caller gives up instead of hanging the GPU)
+// false: the bytes did not arrive within ~2 s (a bug or a dead peer CTA; the caller gives up instead of hanging the GPU).
+// Generous on purpose: under compute-sanitizer a peer CTA can be three orders of magnitude slower than usual.
 __device__ __forceinline__ bool rc_mbar_wait(unsigned mbar, unsigned parity) {
     const long long t0 = clock64();
     for (;;) {
         unsigned ok;
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
         if (ok) return true;
-        if (clock64() - t0 > 400000000ll) return false;
+        if (clock64() - t0 > 4000000000ll) return false;
     }
 }
 __device__ __forceinline__ void rc_sta_v4(unsigned addr, uint4 v, unsigned mbar) {
