@@ -85,7 +85,6 @@ __device__ __forceinline__ unsigned rc_map(const void *p, unsigned rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void rc_st_u64(unsigned addr, u64 v) { asm volatile("st.shared::cluster.u64 [%0], %1;" :: "r"(addr), "l"(v) : "memory"); }
 __device__ __forceinline__ void rc_st_u32(unsigned addr, unsigned v) { asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void rc_cp16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
