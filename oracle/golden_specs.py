@@ -40,6 +40,8 @@ SPECS = {
     "g3_m128_n12000_s1_k2048": ("tick", dict(M=128, N=12000, seed=1), 2048, None),
     "g1_m256_n60000_s1_k16384": ("gossip", dict(M=256, N=60000, seed=1), 16384, None),
     "g1_m1024_n20000_s1_k8192": ("gossip", dict(M=1024, N=20000, seed=1), 8192, None),
+    # a member whose root arrives ~48 rounds late (its chain starts further behind than the round kernels' mirror)
+    "g4_m9_n6000_join3000_s77_k2500": ("late_joiner", dict(M=9, N=6000, join_at=3000, seed=77), 2500, None),
 }
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),

@@ -159,6 +159,30 @@ def tick(M: int, N: int, seed: int = 1) -> Trace:
     return _finish(M, p0, p1, cr, seed, "G3(M=%d,N=%d,seed=%d)" % (M, N, seed))
 
 
+def late_joiner(M: int, N: int, join_at: int, seed: int = 1) -> Trace:
+    """G4: gossip among members 0..M-2; member M-1 creates its root only after ``join_at`` events (dozens of rounds
+    in) and gossips like the others from then on: its chain starts far more rounds behind than the round kernels mirror
+    in shared memory (swirld_rcluster.cuh hands such a chunk to the grid-wide kernel)."""
+    assert M >= 3 and M - 1 <= join_at < N
+    rng = np.random.default_rng(seed)
+    p0, p1, cr, head = [], [], [], {}
+    for c in range(M - 1):
+        head[c] = len(cr); p0.append(-1); p1.append(-1); cr.append(c)
+    while len(cr) < N:
+        if len(cr) == join_at:
+            c = M - 1
+            head[c] = len(cr); p0.append(-1); p1.append(-1); cr.append(c)
+            continue
+        act = sorted(head)
+        c = int(act[rng.integers(len(act))])
+        o = int(act[rng.integers(len(act))])
+        if o == c:
+            continue
+        p0.append(head[c]); p1.append(head[o]); cr.append(c)
+        head[c] = len(cr) - 1
+    return _finish(M, np.array(p0, np.int32), np.array(p1, np.int32), np.array(cr, np.int32), seed, "late-joiner")
+
+
 def chunks(n: int, k: int):
     """The call schedule: consecutive [first, first+count) slices of K events,
     one (divide_rounds, decide_fame, find_order) triple per slice

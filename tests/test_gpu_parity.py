@@ -82,26 +82,8 @@ def test_engine_matches_oracle_tick_and_tied(M, N, K, seed, impl):
 
 
 def _late_joiner(M, N, join_at, seed):
-    """Gossip among members 0..M-2; member M-1 creates its root only after `join_at` events (dozens of rounds in):
-    its chain starts more rounds behind than the round kernels mirror in shared memory."""
     from swirld_b200 import traces
-    rng = np.random.default_rng(seed)
-    p0, p1, cr, head = [], [], [], {}
-    for c in range(M - 1):
-        head[c] = len(cr); p0.append(-1); p1.append(-1); cr.append(c)
-    while len(cr) < N:
-        if len(cr) == join_at:
-            c = M - 1
-            head[c] = len(cr); p0.append(-1); p1.append(-1); cr.append(c)
-            continue
-        act = sorted(head)
-        c = int(act[rng.integers(len(act))])
-        o = int(act[rng.integers(len(act))])
-        if o == c:
-            continue
-        p0.append(head[c]); p1.append(head[o]); cr.append(c)
-        head[c] = len(cr) - 1
-    return traces._finish(M, np.array(p0, np.int32), np.array(p1, np.int32), np.array(cr, np.int32), seed, "late-joiner")
+    return traces.late_joiner(M, N, join_at, seed)
 
 
 @pytest.mark.parametrize("M,N,join_at,K", [(9, 6000, 3000, 6000), (9, 6000, 3000, 2500), (33, 20000, 14000, 4096)])
